@@ -1,0 +1,1 @@
+"""oracle shim package (see oracle/shim/README.md)."""
