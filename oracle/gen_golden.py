@@ -84,6 +84,7 @@ def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, verbose=True):
     W = tab.W
     ref_ports, ref_nbr, ref_dist, ref_prev, ref_nintra, ref_intra0 = [], [], [], [], [], []
     ref_act, ref_sw = [], []
+    ref_rn, ref_rn_off = [], [0]
     for si, name in enumerate(names):
         sw = rn.get_switch_on_position(name2switch_id(name))
         ports = sw.get_port_nodes()
@@ -93,6 +94,8 @@ def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, verbose=True):
             nsw, nport = sw.port2neighbor[p]
             ref_nbr.append(pid[nport])
             ref_dist.append(rn.get_port_distance(p, nport))
+            ref_rn.extend(rn.rail_graph.get_edge_data(p, nport)["rail_nodes"])
+            ref_rn_off.append(len(ref_rn))
             prev = rn.rail_graph.nodes.data("rail_prev_node")[p]
             ref_prev.append(prev[0] * W + prev[1])
             intra = [e[1] for e in rn.rail_graph.edges(p) if (int(e[1][0]), int(e[1][1])) == sw.id and e[1] != nport]
@@ -109,6 +112,8 @@ def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, verbose=True):
     out["ref_port_nintra"] = np.array(ref_nintra, np.int32)
     out["ref_port_intra0"] = np.array(ref_intra0, np.int32)
     out["ref_actions"] = np.array(ref_act, np.int32)
+    out["ref_rail_nodes"] = np.array(ref_rn, np.int32).reshape(-1, 2)
+    out["ref_rail_nodes_off"] = np.array(ref_rn_off, np.int32)
 
     # ------------------------------------------------------------------ F6 against the vendored patch
     vend = _load_vendored_distance_map()
