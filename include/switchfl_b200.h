@@ -1,0 +1,163 @@
+/* switchfl_b200.h -- C-ABI of the B200 backend for SwitchFL's lockstep hot path.
+ *
+ * The reference (AI4REALNET/network-distributed-q-learning) is pure Python and has no FFI of its own;
+ * the seam this library sits behind is the pair of Python classes used by main.py / test_model.py /
+ * hyperparam_tuning.py.  Each entry point names the reference interface it
+ * replaces (paths relative to the reference repository root).
+ *
+ * Conventions: every function returns 0 on success or a negative SFL_E_* code and never throws; all
+ * bulk buffers are CALLER-OWNED device pointers (the Python host allocates them as torch tensors) and
+ * the library never frees them; only the small map-constant block is owned by the context.  One
+ * context per GPU per map, driven from one host thread; work is enqueued on the caller's stream
+ * (a cudaStream_t passed as void*).  There is no CPU path: without a CUDA device sfl_create fails.
+ */
+#ifndef SWITCHFL_B200_H
+#define SWITCHFL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFL_ABI_VERSION 1
+
+enum {
+  SFL_OK = 0,
+  SFL_E_ARG = -1,       /* bad argument / unsupported size                                   */
+  SFL_E_CUDA = -2,      /* CUDA runtime error (see sfl_last_error)                           */
+  SFL_E_NOMEM = -3,     /* caller buffer too small                                           */
+  SFL_E_STATE = -4      /* call order (e.g. run before bind)                                 */
+};
+
+/* per-environment error bits, reported in sfl_env_counters.err (the reference raises instead)       */
+enum {
+  SFL_ERR_NO_TRAIN_AT_SWITCH = 1,   /* observer.py:294-307                                          */
+  SFL_ERR_INF_DISTANCE = 2,         /* observer.py:35-36  ValueError                                 */
+  SFL_ERR_Q_FULL = 4,               /* per-env Q hash table full                                     */
+  SFL_ERR_PEND_FULL = 8,            /* pending-update list of a train full (distr_q.py:340-342)      */
+  SFL_ERR_PLAN_FULL = 16,           /* train_action_plan longer than 4                               */
+  SFL_ERR_REPLAY_UNDERRUN = 32,     /* replay action stream exhausted                                */
+  SFL_ERR_BAD_ACTION = 64           /* switch_env.py:213-215 assertion                               */
+};
+
+/* run modes (sfl_run) */
+enum {
+  SFL_MODE_LEARN = 0,    /* distr_q.py:296-366  epsilon-greedy + Q-update (Philox instead of PCG64)  */
+  SFL_MODE_GREEDY = 1,   /* distr_q.py:195-224  test(): max_action only, no update                   */
+  SFL_MODE_REPLAY = 2    /* learn() with the actions (and malfunction events) of a recorded trace    */
+};
+
+/* Map + line + timetable constants, all HOST pointers; copied by sfl_create.
+ * Replaces the construction work of ASyncSwitchEnv.__init__ -> RailNetwork.__init__
+ * (switch_env.py:30-52, rail_network.py:84-133) and the per-reset constants of switch_env.py:93-158;
+ * the tables are produced by railmap.py (rows A0, F6, Q4 of SURVEY.md section 8a).                   */
+typedef struct sfl_map_desc {
+  int32_t H, W;                 /* grid size (square: rail_graph.py:43-48)                            */
+  int32_t S, NP, NA, T, NT;     /* switches, ports, moving actions (sum of A-1), trains, targets      */
+  int32_t max_episode_steps;    /* flatland timetable (flatland_patch/timetable_generators.py:94-101) */
+  const uint16_t *grid;         /* [H*W] flatland 16-bit transitions                                  */
+  const int32_t *cell_switch;   /* [H*W] switch index or -1                                           */
+  const int32_t *sw_P, *sw_A, *sw_port0, *sw_act0;   /* [S], [S], [S+1], [S+1]                        */
+  const int32_t *port_nbr, *port_dist, *port_n_intra, *port_intra0;   /* [NP]                         */
+  const int32_t *act_in, *act_out, *act_move;        /* [NA] local port indices, RailEnvActions       */
+  const int32_t *init_cell, *init_dir, *target_cell, *ed, *la;        /* [T]                          */
+  const int32_t *first_port, *first_dist, *init_delay, *tgt_index;    /* [T] (switch_env.py:507-568)  */
+  const int32_t *dist;          /* [NT*H*W*4] distance map, 0x3FFFFFFF = unreachable                  */
+  const int8_t *qinit_act;      /* [NP*NT] optimistic action or -1 (distr_q.py:81-181)                */
+  const uint8_t *qinit_final;   /* [NP*NT] 1 -> 1000. (last leg), 0 -> 500.                           */
+} sfl_map_desc;
+
+typedef struct sfl_config {
+  int32_t n_envs;
+  int32_t q_cap;                /* Q hash rows per environment, power of two                          */
+  int32_t pend_cap;             /* pending updates per train (update_dict, distr_q.py:283)            */
+  int32_t max_steps;            /* ASyncSwitchEnv max_steps (100000 in every script)                  */
+  int32_t dec_cap, tick_cap;    /* trace capacities per env (0 = tracing off)                         */
+  int32_t ep_cap;               /* episode-log capacity per env                                       */
+  int32_t act_cap, ev_cap;      /* replay capacities per env                                          */
+  int32_t trace_sem;            /* 1: also log the semaphore table after each decision                */
+} sfl_config;
+
+/* DistrQLearning.__init__ arguments (distr_q.py:32) + MalfunctionParameters (main.py:28-33), per env */
+typedef struct sfl_hparams {
+  double gamma, epsilon, epsilon_decay_rate, lr, lr_decay_rate, default_q;
+  uint64_t seed;                /* Philox key                                                         */
+  uint32_t malf_threshold;      /* floor((1 - exp(-rate)) * 2^32), 0 = no malfunctions                */
+  int32_t malf_min, malf_max;   /* duration = min + U{0..max-min} + 1                                 */
+  int32_t episodes;             /* halt after this many episodes since sfl_reset (<0: never)          */
+  int32_t episode_base;         /* global index of the first episode after sfl_reset (RNG stream offset) */
+  int32_t reserved;
+} sfl_hparams;
+
+/* byte sizes of the caller-owned buffers for a (map, config) pair */
+typedef struct sfl_sizes {
+  uint64_t state_bytes;         /* env state incl. Q tables                                           */
+  uint64_t env_stride;          /* bytes per env inside state                                         */
+  uint64_t hparams_bytes;       /* n_envs * sizeof(sfl_hparams)                                       */
+  uint64_t trace_dec_bytes, trace_tick_bytes, trace_sem_bytes;
+  uint64_t ep_log_bytes, ep_delay_bytes;
+  uint64_t replay_act_bytes, replay_ev_bytes;
+  uint64_t counters_bytes;      /* n_envs * sizeof(sfl_env_counters)                                  */
+  int32_t q_stride;             /* doubles per Q row (1 key slot + A_max)                             */
+  int32_t a_max;
+} sfl_sizes;
+
+typedef struct sfl_buffers {    /* all device pointers; optional ones may be NULL                     */
+  void *state; void *hparams; void *counters;
+  void *trace_dec; void *trace_tick; void *trace_sem;
+  void *ep_log; void *ep_delay;
+  void *replay_act; void *replay_ev;
+} sfl_buffers;
+
+typedef struct sfl_env_counters {      /* written by sfl_run for every env                            */
+  uint64_t decisions, ticks, train_ticks;   /* lifetime totals                                        */
+  int32_t episodes, err, q_rows, halted;
+  int32_t n_dec_logged, n_tick_logged, n_ep_logged, elapsed;
+} sfl_env_counters;
+
+typedef struct sfl_dec_rec {           /* one switch-agent decision (trace)                           */
+  int32_t ep, tick, sw, train;
+  uint32_t key;                        /* dense state index                           */
+  int32_t mask, action, next_sw, reward, done;
+  uint64_t arrived;
+} sfl_dec_rec;
+
+typedef struct sfl_tick_rec { int32_t pos; int8_t dir, state; int16_t malf; } sfl_tick_rec;
+typedef struct sfl_ep_rec { double cum_reward; int32_t decisions, arrived, num_malfunctions, ticks; } sfl_ep_rec;
+
+int sfl_abi_version(void);
+const char *sfl_last_error(void);
+
+/* sizes of everything the caller must allocate */
+int sfl_query_sizes(const sfl_map_desc *map, const sfl_config *cfg, sfl_sizes *out);
+
+/* replaces ASyncSwitchEnv(rail_env, ...) + DistrQLearning(env, ...)   (main.py:51-60) */
+int sfl_create(const sfl_map_desc *map, const sfl_config *cfg, int device, void **ctx);
+int sfl_destroy(void *ctx);
+int sfl_bind(void *ctx, const sfl_buffers *bufs);
+
+/* zero state + mark every env "needs reset"; the first sfl_run performs env.reset (switch_env.py:93-158)
+ * on the device.  keep_q != 0 keeps Q tables and interaction counters (a new learn()/test() call).     */
+int sfl_reset(void *ctx, int keep_q, void *stream);
+
+/* enable the optimistic initialisation of distr_q.py:299-300 for rows created from now on           */
+int sfl_enable_q_init(void *ctx, int on);
+
+/* advance every env by up to max_ticks flatland ticks (all decisions in between included);
+ * replaces the loop body of DistrQLearning.learn / test  (distr_q.py:302-362, 199-224)               */
+int sfl_run(void *ctx, int mode, int max_ticks, void *stream);
+
+/* sum of decisions over all envs after the last run (device reduction, 8-byte D2H)                   */
+int sfl_total_decisions(void *ctx, uint64_t *decisions, uint64_t *ticks, void *stream);
+
+/* Q-table export for distr_q_model.pkl (distr_q.py:492-523): rows of env `env` as (key, A_max values) */
+int sfl_export_q(void *ctx, int env, uint32_t *keys_host, double *vals_host, int cap_rows, int *n_rows, void *stream);
+/* Q-table import (distr_q.py:510-527 load) */
+int sfl_import_q(void *ctx, int env, const uint32_t *keys_host, const double *vals_host, int n_rows, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

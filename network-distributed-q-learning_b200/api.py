@@ -1,0 +1,277 @@
+"""Drop-in surface: the two classes main.py / test_model.py / eval.py / hyperparam_tuning.py construct
+(SURVEY.md section 8b), batched over B lockstep environments on one GPU.
+
+    rail_env = RailEnv(fixture)                                   # replaces main.py:36-49 (flatland generators)
+    env      = ASyncSwitchEnv(rail_env, max_steps=100_000, n_envs=4096)          # main.py:51
+    model    = DistrQLearning(env=env, gamma=1., epsilon=.5, ..., seed=450565)   # main.py:53-60
+    model.learn(num_episodes, out_dir, checkpoint_freq, exploit_freq)            # main.py:63
+    model.save(os.path.join(out_dir, "distr_q_model.pkl"))                       # main.py:66
+
+Environment ``i`` is an independent learner with seed ``seed + i`` (hyperparam_tuning.py's process fan-out
+becomes the env axis; per-env hyper-parameter arrays give the grid).  The decision loop itself
+(distr_q.py:302-362) runs inside the CUDA kernel; the host only launches chunks and collects metrics.
+Outputs keep the reference's file names and dict layout (distr_q.py:288-294, 368-375, 521-523).
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import time
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .backend import MODE_GREEDY, MODE_LEARN, Engine, RailMap
+
+
+class MalfunctionParameters:
+    """flatland.envs.malfunction_generators.MalfunctionParameters (main.py:28-32)."""
+
+    def __init__(self, malfunction_rate=0.0, min_duration=0, max_duration=0):
+        self.malfunction_rate, self.min_duration, self.max_duration = malfunction_rate, min_duration, max_duration
+
+
+class ParamMalfunctionGen:
+    def __init__(self, parameters: MalfunctionParameters):
+        self.parameters = parameters
+
+
+class RailEnv:
+    """Fixture-backed stand-in for the flatland RailEnv constructor lines (main.py:36-49): the map, line
+    and timetable come from a fixture dict / .npz (see mapgen.py) instead of the flatland generators."""
+
+    def __init__(self, fixture, malfunction_generator=None, **_ignored):
+        if isinstance(fixture, str):
+            from .mapgen import load_fixture
+            fixture = load_fixture(fixture)
+        self.fixture = dict(fixture)
+        if malfunction_generator is not None:
+            p = getattr(malfunction_generator, "parameters", malfunction_generator)
+            self.fixture["malfunction_rate"] = float(p.malfunction_rate)
+            self.fixture["min_duration"] = int(p.min_duration)
+            self.fixture["max_duration"] = int(p.max_duration)
+        self.height, self.width = self.fixture["grid"].shape
+        self._elapsed_steps = 0
+
+    def get_num_agents(self) -> int:
+        return len(self.fixture["init_dir"])
+
+
+class ASyncSwitchEnv:
+    """Batched counterpart of switch_env.py:605-678.  Holds the map tables and the engine; the AEC
+    per-decision protocol (agent_iter / last / step) is executed on the device by the learner's kernel."""
+
+    def __init__(self, rail_env: RailEnv, max_steps: int = 200, render_mode=None, observer=None, seed=None,
+                 n_envs: int = 1, device: str = "cuda:0", q_cap: int = 1024, ep_cap: int = 128, _engine_kwargs=None):
+        self.rail_env = rail_env
+        self.max_steps = max_steps
+        self.render_mode = render_mode
+        self.seed = seed
+        self.n_envs = int(n_envs)
+        self.rail_map = RailMap(rail_env.fixture)
+        self.possible_agents = self.rail_map.tab.switch_names()          # switch_env.py:51-52
+        self.agents = self.possible_agents
+        self.engine = Engine(self.rail_map, n_envs=self.n_envs, device=device, q_cap=q_cap, max_steps=max_steps, ep_cap=ep_cap,
+                             **(_engine_kwargs or {}))
+        # the seven wall-clock accumulators main.py:72-78 prints (switch_env.py:67-73); the device loop has no
+        # per-phase split, so the kernel time is booked on step_time and resets on reset_total_time
+        self.flatland_step_time = self.step_time = self.last_time = 0.0
+        self.action_selection_time = self.update_time = self.reset_time = self.reset_total_time = 0.0
+        self.num_malfunctions = 0
+        self.train_to_last_node: Dict[int, tuple] = {}
+
+    def action_space_n(self, agent: str) -> int:
+        return int(self.rail_map.tab.sw_A[self.agents.index(agent)])
+
+    def close(self):
+        pass
+
+
+class DistrQLearning:
+    """Batched counterpart of distr_q.py:11-527."""
+
+    def __init__(self, env: ASyncSwitchEnv, gamma=1.0, epsilon=0.4, epsilon_decay_rate=0.0, lr=0.4, lr_decay_rate=0.0,
+                 default_q=0.0, seed=450565, seeds: Optional[Sequence[int]] = None):
+        self.env = env
+        self.gamma, self.initial_epsilon, self.epsilon_decay_rate = gamma, epsilon, epsilon_decay_rate
+        self.initial_lr, self.lr_decay_rate, self.default_q = lr, lr_decay_rate, default_q
+        self.seed = seed
+        self.seeds = (np.asarray(seeds, np.uint64) if seeds is not None
+                      else np.arange(env.n_envs, dtype=np.uint64) + np.uint64(seed))
+        self.ticks_per_launch = 512
+        self.primary_env = 0                 # the env whose curves / Q-table go to the reference-named files
+        self.q_table: Dict[tuple, List[float]] = {}
+        self.total_decisions = 0
+        self._q_inited = False
+        self._table_dirty = False            # device tables hold rows created before q-init (load() / test())
+        self._stream_fresh = True
+
+    # ------------------------------------------------------------------ internals
+    def _hparams(self, episodes: int, episode_base: int = 0):
+        self.env.engine.set_hparams(gamma=self.gamma, epsilon=self.initial_epsilon, epsilon_decay_rate=self.epsilon_decay_rate,
+                                    lr=self.initial_lr, lr_decay_rate=self.lr_decay_rate, default_q=self.default_q,
+                                    seeds=self.seeds, episodes=episodes, episode_base=episode_base)
+
+    def _run_until_halted(self, mode: int) -> np.ndarray:
+        eng = self.env.engine
+        t0 = time.time()
+        while True:
+            eng.run(mode, self.ticks_per_launch)
+            c = eng.counters()
+            if c["err"].any():
+                eng.check_errors()
+            if (c["halted"] == 1).all():
+                break
+        self.env.step_time += time.time() - t0
+        self.total_decisions += int(c["decisions"].sum())
+        return c
+
+    def _apply_q_init_to_existing_rows(self):
+        """distr_q.py:156-158,179-181 ASSIGN the initial rows at t == 0, overwriting whatever load()/test() put there."""
+        eng = self.env.engine
+        init_rows = self.env.rail_map.q_init_rows(self.default_q)
+        for i in range(self.env.n_envs):
+            q = eng.export_q(i)
+            hit = [k for k in q if k in init_rows]
+            if hit:
+                for k in hit:
+                    q[k] = list(init_rows[k])
+                eng.import_q(i, q)
+
+    def learn_chunk(self, max_ticks: Optional[int] = None) -> np.ndarray:
+        """Streaming API: upload the per-env hyper-parameter block, advance every environment by up to ``max_ticks``
+        flatland ticks of learn() (no episode limit) and return the per-env counters (host array).
+        bench.py times this call for its end-to-end number."""
+        eng = self.env.engine
+        if self._stream_fresh:
+            self._hparams(-1)
+            eng.reset()
+            eng.enable_q_init(True)
+            self._q_inited = True
+            self._stream_fresh = False
+        else:
+            eng._upload("hparams", eng.hparams)
+        eng.run(MODE_LEARN, self.ticks_per_launch if max_ticks is None else max_ticks)
+        return eng.counters()
+
+    # ------------------------------------------------------------------ distr_q.py:244-379
+    def learn(self, num_episodes: int, out_dir: Optional[str], checkpoint_freq: int, exploit_freq: Optional[int] = None):
+        eng, env = self.env.engine, self.env
+        B, T = env.n_envs, env.rail_map.trains.T
+        p = self.primary_env
+        if out_dir:
+            os.makedirs(out_dir, exist_ok=True)
+        cum_reward = np.zeros((B, num_episodes))
+        arrived = np.zeros((B, num_episodes), np.int32)
+        delays = np.zeros((B, num_episodes, T))
+        num_malf = np.zeros((B, num_episodes), np.int32)
+        cum_reward_exploit, arrived_exploit = [], []
+        t_start = time.time()
+        # pause points: the reference exploits / checkpoints BEFORE episode t when (t+1) % freq == 0 (distr_q.py:278-294)
+        pauses = sorted({t for t in range(num_episodes)
+                         if (exploit_freq and (t + 1) % exploit_freq == 0) or (checkpoint_freq and (t + 1) % checkpoint_freq == 0)}
+                        | {num_episodes})
+        done, first = 0, True
+        for cut in pauses:
+            while done < cut:                                   # run episodes [done, cut) in ep_cap-sized launches
+                seg = min(cut - done, eng.cfg.ep_cap)
+                self._hparams(seg, episode_base=done)
+                if first:
+                    t0 = time.time()
+                    eng.reset(keep_q=self._table_dirty, keep_interactions=False)     # agent_num_interactions is per learn() (:263)
+                    if self._table_dirty:
+                        self._apply_q_init_to_existing_rows()
+                    eng.enable_q_init(True)                                           # distr_q.py:299-300
+                    self._q_inited = True
+                    first = False
+                    env.reset_total_time += time.time() - t0
+                else:
+                    eng.reset(keep_q=True, keep_interactions=True)
+                self._run_until_halted(MODE_LEARN)
+                _, log, dl = eng.episode_log()
+                cum_reward[:, done:done + seg] = log["cum_reward"][:, :seg]
+                arrived[:, done:done + seg] = log["arrived"][:, :seg]
+                num_malf[:, done:done + seg] = log["num_malfunctions"][:, :seg]
+                delays[:, done:done + seg] = dl[:, :seg]
+                done += seg
+            if cut >= num_episodes:
+                break
+            if exploit_freq and (cut + 1) % exploit_freq == 0:
+                r, a, _ = self.test(out_dir=None, plot=False, save_outputs=False, _batched=True)
+                cum_reward_exploit.append(r)
+                arrived_exploit.append(a)
+            if checkpoint_freq and (cut + 1) % checkpoint_freq == 0 and out_dir:
+                self.q_table = eng.export_q(p, include_init=self._q_inited, default_q=self.default_q)
+                self.save(os.path.join(out_dir, f"checkpoint_{cut + 1}.pkl"))
+                np.savez_compressed(os.path.join(out_dir, f"cum_reward_checkpoint_{cut + 1}.npz"), x=cum_reward[p])
+                np.savez_compressed(os.path.join(out_dir, f"arrived_trains_checkpoint_{cut + 1}.npz"), x=arrived[p, :cut])
+                np.savez_compressed(os.path.join(out_dir, f"delays_checkpoint_{cut + 1}.npz"), x=delays[p, :cut])
+                np.savez_compressed(os.path.join(out_dir, f"trains_at_dest_checkpoint_{cut + 1}.npz"), x=[])
+                np.savez_compressed(os.path.join(out_dir, f"num_malfunctions_checkpoint_{cut + 1}.npz"), x=num_malf[p, :cut])
+        self._table_dirty = True
+        self.q_table = eng.export_q(p, include_init=self._q_inited, default_q=self.default_q)
+        self.metrics = dict(cum_reward=cum_reward, arrived_trains=arrived, delays=delays, num_malfunctions=num_malf,
+                            cum_reward_exploit=np.array(cum_reward_exploit), arrived_trains_exploit=np.array(arrived_exploit),
+                            wall_s=time.time() - t_start)
+        if out_dir:
+            np.savez_compressed(os.path.join(out_dir, "cum_reward.npz"), x=cum_reward[p])
+            np.savez_compressed(os.path.join(out_dir, "arrived_trains.npz"), x=arrived[p])
+            np.savez_compressed(os.path.join(out_dir, "delays.npz"), x=delays[p])
+            np.savez_compressed(os.path.join(out_dir, "num_malfunctions.npz"), x=num_malf[p])
+            if exploit_freq is not None:
+                np.savez_compressed(os.path.join(out_dir, "cum_reward_exploit.npz"), x=[r[p] for r in cum_reward_exploit])
+                np.savez_compressed(os.path.join(out_dir, "arrived_trains_exploit.npz"), x=[a[p] for a in arrived_exploit])
+            np.savez_compressed(os.path.join(out_dir, "batched_metrics.npz"), cum_reward=cum_reward, arrived_trains=arrived,
+                                delays=delays, num_malfunctions=num_malf, seeds=self.seeds)
+        if num_episodes:
+            env.num_malfunctions = int(num_malf[p, -1])
+            env.train_to_last_node = {h: (None, float(delays[p, -1, h])) for h in range(T)}
+        env.close()
+
+    # ------------------------------------------------------------------ distr_q.py:184-241
+    def test(self, out_dir, plot=False, save_outputs=True, _batched=False):
+        """Greedy rollout of every environment (one episode each); returns env 0's (cum_reward, arrived, delays)
+        like the reference unless ``_batched``."""
+        eng, env = self.env.engine, self.env
+        T = env.rail_map.trains.T
+        self._hparams(1)
+        eng.reset(keep_q=True, keep_interactions=True)
+        eng.enable_q_init(self._q_inited)
+        self._run_until_halted(MODE_GREEDY)
+        self._table_dirty = True
+        _, log, dl = eng.episode_log()
+        cum, arr, delays = log["cum_reward"][:, 0].copy(), log["arrived"][:, 0].copy(), dl[:, 0].astype(np.float64)
+        p = self.primary_env
+        if save_outputs:
+            print(f"Terminated in {int(log['decisions'][p, 0])} steps ({int(log['ticks'][p, 0])} flatland steps), "
+                  f"cumulative reward = {cum[p]}")
+            print(f"Arrived trains: {int(arr[p])} / {T}")
+            print(f"Delays: {list(delays[p])}")
+            print(f"Num malfunctions: {int(log['num_malfunctions'][p, 0])}")
+            if out_dir:
+                np.savez_compressed(os.path.join(out_dir, "cum_reward.npz"), x=cum[p])
+                np.savez_compressed(os.path.join(out_dir, "delays.npz"), x=list(delays[p]))
+        if _batched:
+            return cum, arr, delays
+        self.q_table = eng.export_q(p, include_init=self._q_inited, default_q=self.default_q)   # test() inserts rows (App. A #15)
+        return float(cum[p]), int(arr[p]), list(delays[p])
+
+    # ------------------------------------------------------------------ distr_q.py:492-527
+    def save(self, filename: str, mode: str = "pickle"):
+        if mode != "pickle":
+            raise AttributeError("only mode='pickle' exists in the reference (distr_q.py:505-508 dispatch to undefined methods)")
+        q = {tuple(np.int64(x) for x in k): list(v) for k, v in self.q_table.items()}   # np.int64 key elements (observer.py:306)
+        with open(filename, "wb") as f:
+            pickle.dump(q, f)
+
+    def load(self, filename: str):
+        with open(filename, "rb") as f:
+            q = pickle.load(f)
+        self.q_table = {tuple(int(x) for x in k): [float(x) for x in v] for k, v in q.items()}
+        eng = self.env.engine
+        self._hparams(-1)
+        eng.reset()
+        for i in range(self.env.n_envs):
+            eng.import_q(i, self.q_table)
+        self._table_dirty = True
+        self._q_inited = False

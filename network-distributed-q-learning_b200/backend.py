@@ -1,0 +1,366 @@
+"""ctypes binding of the C-ABI (include/switchfl_b200.h) + the batched engine object the drop-in classes use.
+
+PyTorch only owns the device buffers (one uint8 tensor per buffer of ``sfl_buffers``); every bit of the
+hot path runs inside ``libswitchfl_b200.so`` (hand-written sm_100a CUDA).  There is no CPU fallback: if
+the library is missing or no CUDA device exists, construction raises.
+
+(``tests/emul`` builds the same C sources for the host to unit-test the per-environment logic on the
+GPU-less build box; it is reachable only through the private ``_emul_lib`` argument used by tests.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import railmap
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libswitchfl_b200.so")
+
+MODE_LEARN, MODE_GREEDY, MODE_REPLAY = 0, 1, 2
+ERR_BITS = {1: "no train at active switch (observer.py:294-307)", 2: "infinite distance to target (observer.py:35-36)",
+            4: "per-env Q table full (raise q_cap)", 8: "pending-update list full (raise pend_cap)",
+            16: "train action plan overflow", 32: "replay action stream exhausted", 64: "invalid action (switch_env.py:213-215)"}
+
+_i32p, _u16p, _i8p, _u8p = C.POINTER(C.c_int32), C.POINTER(C.c_uint16), C.POINTER(C.c_int8), C.POINTER(C.c_uint8)
+
+
+class MapDesc(C.Structure):
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("S", C.c_int32), ("NP", C.c_int32), ("NA", C.c_int32), ("T", C.c_int32),
+                ("NT", C.c_int32), ("max_episode_steps", C.c_int32), ("grid", _u16p), ("cell_switch", _i32p),
+                ("sw_P", _i32p), ("sw_A", _i32p), ("sw_port0", _i32p), ("sw_act0", _i32p),
+                ("port_nbr", _i32p), ("port_dist", _i32p), ("port_n_intra", _i32p), ("port_intra0", _i32p),
+                ("act_in", _i32p), ("act_out", _i32p), ("act_move", _i32p),
+                ("init_cell", _i32p), ("init_dir", _i32p), ("target_cell", _i32p), ("ed", _i32p), ("la", _i32p),
+                ("first_port", _i32p), ("first_dist", _i32p), ("init_delay", _i32p), ("tgt_index", _i32p),
+                ("dist", _i32p), ("qinit_act", _i8p), ("qinit_final", _u8p)]
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_envs", "q_cap", "pend_cap", "max_steps", "dec_cap", "tick_cap", "ep_cap",
+                                         "act_cap", "ev_cap", "trace_sem")]
+
+
+class Sizes(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("state_bytes", "env_stride", "hparams_bytes", "trace_dec_bytes", "trace_tick_bytes",
+                                          "trace_sem_bytes", "ep_log_bytes", "ep_delay_bytes", "replay_act_bytes",
+                                          "replay_ev_bytes", "counters_bytes")] + [("q_stride", C.c_int32), ("a_max", C.c_int32)]
+
+
+class Buffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("state", "hparams", "counters", "trace_dec", "trace_tick", "trace_sem", "ep_log",
+                                          "ep_delay", "replay_act", "replay_ev")]
+
+
+HPARAMS_DT = np.dtype([("gamma", "f8"), ("epsilon", "f8"), ("epsilon_decay_rate", "f8"), ("lr", "f8"), ("lr_decay_rate", "f8"),
+                       ("default_q", "f8"), ("seed", "u8"), ("malf_threshold", "u4"), ("malf_min", "i4"), ("malf_max", "i4"),
+                       ("episodes", "i4"), ("episode_base", "i4"), ("reserved", "i4")])
+COUNTERS_DT = np.dtype([("decisions", "u8"), ("ticks", "u8"), ("train_ticks", "u8"), ("episodes", "i4"), ("err", "i4"),
+                        ("q_rows", "i4"), ("halted", "i4"), ("n_dec_logged", "i4"), ("n_tick_logged", "i4"),
+                        ("n_ep_logged", "i4"), ("elapsed", "i4")])
+DEC_DT = np.dtype([("ep", "i4"), ("tick", "i4"), ("sw", "i4"), ("train", "i4"), ("key", "u4"), ("mask", "i4"), ("action", "i4"),
+                   ("next_sw", "i4"), ("reward", "i4"), ("done", "i4"), ("arrived", "u8")])
+TICK_DT = np.dtype([("pos", "i4"), ("dir", "i1"), ("state", "i1"), ("malf", "i2")])
+EP_DT = np.dtype([("cum_reward", "f8"), ("decisions", "i4"), ("arrived", "i4"), ("num_malfunctions", "i4"), ("ticks", "i4")])
+assert HPARAMS_DT.itemsize == 80 and COUNTERS_DT.itemsize == 56 and DEC_DT.itemsize == 48 and TICK_DT.itemsize == 8 and EP_DT.itemsize == 24
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(path)
+    lib.sfl_last_error.restype = C.c_char_p
+    lib.sfl_query_sizes.argtypes = [C.POINTER(MapDesc), C.POINTER(Config), C.POINTER(Sizes)]
+    lib.sfl_create.argtypes = [C.POINTER(MapDesc), C.POINTER(Config), C.c_int, C.POINTER(C.c_void_p)]
+    lib.sfl_destroy.argtypes = [C.c_void_p]
+    lib.sfl_bind.argtypes = [C.c_void_p, C.POINTER(Buffers)]
+    lib.sfl_reset.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.sfl_enable_q_init.argtypes = [C.c_void_p, C.c_int]
+    lib.sfl_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.sfl_total_decisions.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
+    lib.sfl_export_q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.c_void_p]
+    lib.sfl_import_q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_int, C.c_void_p]
+    if lib.sfl_abi_version() != 1:
+        raise RuntimeError("switchfl_b200 ABI version mismatch")
+    return lib
+
+
+def malf_threshold(rate: float) -> int:
+    """ParamMalfunctionGen probability 1 - exp(-rate) as a 32-bit threshold."""
+    if rate <= 0:
+        return 0
+    return min(int((1.0 - math.exp(-rate)) * 4294967296.0), 0xFFFFFFFF)
+
+
+class RailMap:
+    """Everything derived from one fixture: port-graph tables, per-train constants, the C descriptor."""
+
+    def __init__(self, fixture: dict):
+        self.fixture = fixture
+        self.tab = railmap.build_switch_tables(fixture["grid"])
+        self.trains = railmap.build_train_tables(self.tab, fixture["init_pos"], fixture["init_dir"], fixture["target"],
+                                                 fixture["earliest_departure"], fixture["latest_arrival"])
+        t, tr = self.tab, self.trains
+        self._keep = {}
+
+        def arr(name, a, dt=np.int32):
+            a = np.ascontiguousarray(a, dtype=dt)
+            self._keep[name] = a
+            return a
+
+        d = MapDesc()
+        d.H, d.W, d.S, d.NP, d.NA, d.T, d.NT = t.H, t.W, t.S, t.NP, len(t.act_in), tr.T, len(tr.targets)
+        d.max_episode_steps = int(fixture["max_episode_steps"])
+        d.grid = arr("grid", t.grid, np.uint16).ctypes.data_as(_u16p)
+        for name, a in (("cell_switch", t.cell_switch), ("sw_P", t.sw_P), ("sw_A", t.sw_A), ("sw_port0", t.sw_port0),
+                        ("sw_act0", t.sw_act0), ("port_nbr", t.port_nbr), ("port_dist", t.port_dist),
+                        ("port_n_intra", t.port_n_intra), ("port_intra0", t.port_intra0), ("act_in", t.act_in),
+                        ("act_out", t.act_out), ("act_move", t.act_move), ("init_cell", tr.init_cell), ("init_dir", tr.init_dir),
+                        ("target_cell", tr.target_cell), ("ed", tr.ed), ("la", tr.la), ("first_port", tr.first_port),
+                        ("first_dist", tr.first_dist), ("init_delay", tr.init_delay), ("tgt_index", tr.tgt_index),
+                        ("dist", tr.dist)):
+            setattr(d, name, arr(name, a).ctypes.data_as(_i32p))
+        d.qinit_act = arr("qinit_act", tr.qinit_act, np.int8).ctypes.data_as(_i8p)
+        d.qinit_final = arr("qinit_final", (tr.qinit_val == 1000.0), np.uint8).ctypes.data_as(_u8p)
+        self.desc = d
+
+    # ---- state-index <-> observation (observer.py:303-306 layout [row, col, sem[P], target[2P], delay[P]])
+    def key_to_obs(self, key: int) -> tuple:
+        t, tr = self.tab, self.trains
+        NT = len(tr.targets)
+        port, rem = divmod(int(key), NT * 48)
+        tgt, rem = divmod(rem, 48)
+        semb, level = divmod(rem, 3)
+        s = int(t.port_switch[port])
+        P = int(t.sw_P[s])
+        cur = port - int(t.sw_port0[s])
+        r, c = t.switch_cells[s]
+        tcell = int(tr.targets[tgt])
+        sem = [(semb >> k) & 1 for k in range(P)]
+        target = [-1] * (2 * P)
+        target[2 * cur], target[2 * cur + 1] = tcell // t.W, tcell % t.W
+        delay = [-1] * P
+        delay[cur] = level
+        return (int(r), int(c), *sem, *target, *delay)
+
+    def obs_to_key(self, obs: Sequence[int]) -> int:
+        t, tr = self.tab, self.trains
+        s = t.switch_cells.index((int(obs[0]), int(obs[1])))
+        P = int(t.sw_P[s])
+        sem = obs[2:2 + P]
+        target = obs[2 + P:2 + 3 * P]
+        delay = obs[2 + 3 * P:2 + 4 * P]
+        cur = [k for k in range(P) if delay[k] >= 0][0]
+        tcell = int(target[2 * cur]) * t.W + int(target[2 * cur + 1])
+        tgt = int(np.where(tr.targets == tcell)[0][0])
+        semb = sum(int(sem[k]) << k for k in range(P))
+        return (((int(t.sw_port0[s]) + cur) * len(tr.targets) + tgt) * 16 + semb) * 3 + int(delay[cur])
+
+    def q_init_rows(self, default_q: float) -> Dict[tuple, List[float]]:
+        """All rows __init_q_table creates (distr_q.py:81-181), as the reference's dict."""
+        t, tr = self.tab, self.trains
+        out = {}
+        NT = len(tr.targets)
+        for port in range(t.NP):
+            s = int(t.port_switch[port])
+            P, A = int(t.sw_P[s]), int(t.sw_A[s])
+            for tgt in range(NT):
+                a = int(tr.qinit_act[port, tgt])
+                if a < 0:
+                    continue
+                for semb in range(1, 1 << P):
+                    for level in range(3):
+                        row = [default_q] * A
+                        row[a] = float(tr.qinit_val[port, tgt])
+                        out[self.key_to_obs(((port * NT + tgt) * 16 + semb) * 3 + level)] = row
+        return out
+
+
+class Engine:
+    """B lockstep environments of one map on one GPU: owns the torch buffers and the C context."""
+
+    def __init__(self, rail_map: RailMap, n_envs: int, device: str = "cuda:0", q_cap: int = 1024, pend_cap: int = 8,
+                 max_steps: int = 100_000, dec_cap: int = 0, tick_cap: int = 0, ep_cap: int = 64, act_cap: int = 0,
+                 ev_cap: int = 0, trace_sem: bool = False, _emul_lib: Optional[str] = None):
+        import torch
+        self.torch = torch
+        self.map = rail_map
+        self.n_envs = int(n_envs)
+        self._emul = _emul_lib is not None
+        if self._emul:
+            self.lib = load_library(_emul_lib)
+            self.device = torch.device("cpu")
+            dev_index = 0
+        else:
+            if not torch.cuda.is_available():
+                raise RuntimeError("switchfl_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+            self.lib = load_library()
+            self.device = torch.device(device)
+            dev_index = self.device.index or 0
+        self.cfg = Config(n_envs=self.n_envs, q_cap=q_cap, pend_cap=pend_cap, max_steps=max_steps, dec_cap=dec_cap,
+                          tick_cap=tick_cap, ep_cap=ep_cap, act_cap=act_cap, ev_cap=ev_cap, trace_sem=int(trace_sem))
+        self.sizes = Sizes()
+        self._ck(self.lib.sfl_query_sizes(C.byref(rail_map.desc), C.byref(self.cfg), C.byref(self.sizes)))
+        self.ctx = C.c_void_p()
+        self._ck(self.lib.sfl_create(C.byref(rail_map.desc), C.byref(self.cfg), dev_index, C.byref(self.ctx)))
+        z = lambda n: torch.zeros(max(int(n), 16), dtype=torch.uint8, device=self.device)
+        s = self.sizes
+        self.buf = {"state": z(s.state_bytes), "hparams": z(s.hparams_bytes), "counters": z(s.counters_bytes),
+                    "trace_dec": z(s.trace_dec_bytes), "trace_tick": z(s.trace_tick_bytes), "trace_sem": z(s.trace_sem_bytes),
+                    "ep_log": z(s.ep_log_bytes), "ep_delay": z(s.ep_delay_bytes), "replay_act": z(s.replay_act_bytes),
+                    "replay_ev": z(s.replay_ev_bytes)}
+        b = Buffers(**{k: v.data_ptr() for k, v in self.buf.items()})
+        self._ck(self.lib.sfl_bind(self.ctx, C.byref(b)))
+        self.hparams = np.zeros(self.n_envs, HPARAMS_DT)
+        self._pinned = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise RuntimeError(f"switchfl_b200 error {rc}: {self.lib.sfl_last_error().decode()}")
+
+    def _stream(self):
+        if self._emul:
+            return None
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _upload(self, name: str, host: np.ndarray):
+        """host -> device through a reusable pinned staging buffer."""
+        torch = self.torch
+        raw = np.ascontiguousarray(host).view(np.uint8).reshape(-1)
+        dst = self.buf[name][:raw.size]
+        if self._emul:
+            dst.copy_(torch.from_numpy(raw))
+            return
+        st = self._pinned.get(name)
+        if st is None or st.numel() < raw.size:
+            st = self._pinned[name] = torch.empty(raw.size, dtype=torch.uint8, pin_memory=True)
+        st[:raw.size].copy_(torch.from_numpy(raw))
+        dst.copy_(st[:raw.size], non_blocking=True)
+
+    def _download(self, name: str, nbytes: Optional[int] = None) -> np.ndarray:
+        t = self.buf[name] if nbytes is None else self.buf[name][:nbytes]
+        return t.cpu().numpy()
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx:
+            self.lib.sfl_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ control
+    def set_hparams(self, gamma=1.0, epsilon=0.4, epsilon_decay_rate=0.0, lr=0.4, lr_decay_rate=0.0, default_q=0.0,
+                    seeds=None, episodes=-1, episode_base=0, malfunction_rate=None, min_duration=None, max_duration=None):
+        """Scalars broadcast; arrays give one value per env (the hyper-parameter / seed grid)."""
+        fx = self.map.fixture
+        hp = self.hparams
+        for k, v in (("gamma", gamma), ("epsilon", epsilon), ("epsilon_decay_rate", epsilon_decay_rate), ("lr", lr),
+                     ("lr_decay_rate", lr_decay_rate), ("default_q", default_q), ("episodes", episodes),
+                     ("episode_base", episode_base)):
+            hp[k] = v
+        hp["seed"] = np.arange(self.n_envs, dtype=np.uint64) if seeds is None else np.asarray(seeds, np.uint64)
+        rate = fx["malfunction_rate"] if malfunction_rate is None else malfunction_rate
+        hp["malf_threshold"] = malf_threshold(float(rate))
+        hp["malf_min"] = fx["min_duration"] if min_duration is None else min_duration
+        hp["malf_max"] = fx["max_duration"] if max_duration is None else max_duration
+        self._upload("hparams", hp)
+
+    def reset(self, keep_q: bool = False, keep_interactions: bool = False):
+        self._ck(self.lib.sfl_reset(self.ctx, int(keep_q) | (int(keep_interactions) << 1), self._stream()))
+
+    def enable_q_init(self, on: bool = True):
+        self._ck(self.lib.sfl_enable_q_init(self.ctx, int(on)))
+
+    def run(self, mode: int, max_ticks: int):
+        self._ck(self.lib.sfl_run(self.ctx, int(mode), int(max_ticks), self._stream()))
+
+    def set_replay(self, actions: Sequence[Sequence[int]], events: Optional[Sequence[np.ndarray]] = None):
+        """actions[i]: the recorded action stream of env i; events[i]: int array [(tick, train, duration)]."""
+        a = np.full((self.n_envs, self.cfg.act_cap), -1, np.int8)
+        for i, s in enumerate(actions):
+            a[i, :len(s)] = s
+        self._upload("replay_act", a)
+        if self.cfg.ev_cap:
+            ev = np.full((self.n_envs, self.cfg.ev_cap, 3), -1, np.int32)
+            for i, e in enumerate(events or []):
+                e = np.asarray(e, np.int32).reshape(-1, 3)
+                e = e[np.lexsort((e[:, 1], e[:, 0]))] if len(e) else e
+                ev[i, :len(e)] = e
+            self._upload("replay_ev", ev)
+
+    # ------------------------------------------------------------------ results
+    def total_decisions(self):
+        d, t = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.sfl_total_decisions(self.ctx, C.byref(d), C.byref(t), self._stream()))
+        return d.value, t.value
+
+    def counters(self) -> np.ndarray:
+        c = self._download("counters", self.n_envs * COUNTERS_DT.itemsize).view(COUNTERS_DT)
+        return c
+
+    def check_errors(self):
+        err = self.counters()["err"]
+        if err.any():
+            i = int(np.nonzero(err)[0][0])
+            msgs = [m for b, m in ERR_BITS.items() if err[i] & b]
+            raise RuntimeError(f"env {i}: {'; '.join(msgs)} ({int((err != 0).sum())} env(s) flagged)")
+
+    def episode_log(self):
+        n = self.counters()["n_ep_logged"]
+        log = self._download("ep_log").view(EP_DT)[:self.n_envs * self.cfg.ep_cap].reshape(self.n_envs, self.cfg.ep_cap)
+        T = self.map.trains.T
+        delays = self._download("ep_delay").view(np.int32)[:self.n_envs * self.cfg.ep_cap * T].reshape(self.n_envs, self.cfg.ep_cap, T)
+        return n, log, delays
+
+    def trace(self, env: int):
+        c = self.counters()[env]
+        T, NP = self.map.trains.T, self.map.tab.NP
+        dec = self._download("trace_dec").view(DEC_DT)[:self.n_envs * self.cfg.dec_cap].reshape(self.n_envs, self.cfg.dec_cap)[env]
+        dec = dec[:min(int(c["n_dec_logged"]), self.cfg.dec_cap)]
+        tick = self._download("trace_tick").view(TICK_DT)[:self.n_envs * self.cfg.tick_cap * T].reshape(self.n_envs, self.cfg.tick_cap, T)[env]
+        tick = tick[:min(int(c["n_tick_logged"]), self.cfg.tick_cap)]
+        sem = None
+        if self.cfg.trace_sem:
+            sem = self._download("trace_sem").view(np.int32)[:self.n_envs * self.cfg.dec_cap * NP * 4]
+            sem = sem.reshape(self.n_envs, self.cfg.dec_cap, NP, 4)[env][:len(dec)]
+        return dec, tick, sem
+
+    def export_q(self, env: int, include_init: bool = False, default_q: Optional[float] = None) -> Dict[tuple, List[float]]:
+        """The reference's q_table dict (distr_q.py:42, pickled by :521-523): obs tuple -> list of A floats."""
+        a_max = self.sizes.a_max
+        cap = self.cfg.q_cap
+        keys = np.zeros(cap, np.uint32)
+        vals = np.zeros((cap, a_max), np.float64)
+        n = C.c_int()
+        self._ck(self.lib.sfl_export_q(self.ctx, env, keys.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                       vals.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(n), self._stream()))
+        out = {}
+        if include_init:
+            out.update(self.map.q_init_rows(float(self.hparams["default_q"][env]) if default_q is None else default_q))
+        t = self.map.tab
+        NT = len(self.map.trains.targets)
+        for k, v in zip(keys[:n.value], vals[:n.value]):
+            A = int(t.sw_A[t.port_switch[int(k) // (NT * 48)]])
+            out[self.map.key_to_obs(int(k))] = [float(x) for x in v[:A]]
+        return out
+
+    def import_q(self, env: int, q: Dict[tuple, List[float]]):
+        a_max = self.sizes.a_max
+        keys = np.zeros(max(len(q), 1), np.uint32)
+        vals = np.zeros((max(len(q), 1), a_max), np.float64)
+        for i, (obs, row) in enumerate(q.items()):
+            keys[i] = self.map.obs_to_key(obs)
+            vals[i, :len(row)] = row
+        self._ck(self.lib.sfl_import_q(self.ctx, env, keys.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                       vals.ctypes.data_as(C.POINTER(C.c_double)), len(q), self._stream()))

@@ -83,7 +83,15 @@ class SwitchFLOracle:
         self.trace = None
 
     # ------------------------------------------------------------------ env: reset (switch_env.py:93-158)
+    def malfunction_schedule(self) -> np.ndarray:
+        """Every applied malfunction event (tick, train, duration) seen so far.  rail_env.reset(random_seed=seed)
+        re-seeds flatland's RNG at every episode (switch_env.py:99), so the schedule repeats per episode and the
+        union over episodes is THE schedule of this seed (replay input of the CUDA path)."""
+        ev = set(self._malf_events) | set(self.rail_env.malfunction_events)
+        return np.array(sorted(ev), np.int32).reshape(-1, 3)
+
     def reset(self, seed=None):
+        self._malf_events = getattr(self, "_malf_events", set()) | set(self.rail_env.malfunction_events)
         self.rail_env.reset(random_seed=seed)
         agents = self.rail_env.agents
         keys = [a.initial_position + (a.initial_direction,) for a in agents]

@@ -1,0 +1,97 @@
+"""GPU (-m gpu): the CUDA path through the C-ABI against the reference goldens and against the oracle."""
+import numpy as np
+import pytest
+
+from switchfl_b200 import backend, mapgen
+from tests._parity import check_replay
+from tests._util import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_engine(rm, **kw):
+    return backend.Engine(rm, device="cuda:0", **kw)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_replay_matches_reference(name):
+    check_replay(name, gpu_engine, n_envs=3)
+
+
+def test_cuda_chunked_launches_equal_one_launch():
+    check_replay("slips24_t6", gpu_engine, n_envs=2, chunk=5)
+
+
+def test_cuda_replay_many_seeds_against_oracle():
+    """64 environments with different seeds: the oracle free-runs, the CUDA path replays each stream."""
+    from oracle.switchfl_oracle import SwitchFLOracle
+    fx, g = load_golden("c1_synth18")
+    rm = backend.RailMap(fx)
+    hp = dict(gamma=0.9, epsilon=0.6, epsilon_decay_rate=0.999, lr=0.2, lr_decay_rate=1.0, default_q=0.5)
+    B, n_ep = 64, 3
+    oracles, acts, evs = [], [], []
+    for i in range(B):
+        o = SwitchFLOracle(fx, rm.tab, seed=1000 + i, **hp)
+        o.enable_trace()
+        o.learn(n_ep)
+        oracles.append(o)
+        acts.append(np.array(o.trace["dec_action"], np.int8))
+        evs.append(o.malfunction_schedule())
+    n_dec = max(len(a) for a in acts)
+    eng = gpu_engine(rm, n_envs=B, q_cap=1024, dec_cap=n_dec + 4, act_cap=n_dec + 4, ev_cap=max(len(e) for e in evs) + 2, ep_cap=n_ep + 1)
+    eng.set_hparams(**hp, seeds=np.arange(B), episodes=n_ep)
+    eng.set_replay(acts, evs)
+    eng.reset()
+    eng.enable_q_init(True)
+    eng.run(backend.MODE_REPLAY, 100000)
+    eng.check_errors()
+    for i, o in enumerate(oracles):
+        dec, _, _ = eng.trace(i)
+        assert np.array_equal(dec["reward"].astype(np.float64), np.array(o.trace["dec_reward"])), i
+        assert np.array_equal(dec["sw"], np.array(o.trace["dec_switch"])), i
+        assert eng.export_q(i, include_init=True) == o.q_table, i
+    eng.close()
+
+
+def test_cuda_learn_4096_envs_properties():
+    """BASELINE config C2 size: free-running learn on 4096 envs; size-independent invariants."""
+    fx, _ = load_golden("c1_synth18")
+    rm = backend.RailMap(fx)
+    B = 4096
+    eng = gpu_engine(rm, n_envs=B, q_cap=1024, ep_cap=8)
+    eng.set_hparams(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0,
+                    seeds=np.arange(B) + 450565, episodes=4)
+    eng.reset()
+    eng.enable_q_init(True)
+    eng.run(backend.MODE_LEARN, 100000)
+    eng.check_errors()
+    c = eng.counters()
+    assert (c["halted"] == 1).all() and (c["episodes"] == 4).all()
+    n, log, delays = eng.episode_log()
+    assert (n == 4).all()
+    assert (log["decisions"][:, :4].sum(axis=1) == c["decisions"]).all()           # bookkeeping closes
+    assert (log["ticks"][:, :4].sum(axis=1) == c["ticks"]).all()
+    assert (log["ticks"][:, :4] <= int(fx["max_episode_steps"])).all()
+    assert (log["arrived"][:, :4] >= 0).all() and (log["arrived"][:, :4] <= 2).all()
+    d, t = eng.total_decisions()
+    assert d == int(c["decisions"].sum()) and t == int(c["ticks"].sum())
+    # same seed -> same trajectory (determinism across launches)
+    eng.reset()
+    eng.run(backend.MODE_LEARN, 100000)
+    c2 = eng.counters()
+    assert np.array_equal(c2["decisions"], c["decisions"]) and np.array_equal(c2["ticks"], c["ticks"])
+    # different seeds explore differently
+    assert len(np.unique(c["decisions"])) > 1
+    q = eng.export_q(0)
+    assert all(np.isfinite(v).all() for v in q.values())
+    eng.close()
+
+
+def test_library_refuses_without_binding():
+    fx, _ = load_golden("loop_chord_7x7")
+    rm = backend.RailMap(fx)
+    eng = gpu_engine(rm, n_envs=1)
+    with pytest.raises(RuntimeError):
+        eng.run(backend.MODE_REPLAY, 1)     # replay without a replay buffer contents -> underrun flagged or arg error
+        eng.check_errors()
+    eng.close()
