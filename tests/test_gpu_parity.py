@@ -87,11 +87,14 @@ def test_cuda_learn_4096_envs_properties():
     eng.close()
 
 
-def test_library_refuses_without_binding():
+def test_replay_underrun_is_reported_loudly():
     fx, _ = load_golden("loop_chord_7x7")
     rm = backend.RailMap(fx)
-    eng = gpu_engine(rm, n_envs=1)
-    with pytest.raises(RuntimeError):
-        eng.run(backend.MODE_REPLAY, 1)     # replay without a replay buffer contents -> underrun flagged or arg error
+    eng = gpu_engine(rm, n_envs=2, act_cap=1)
+    eng.set_hparams(episodes=1)
+    eng.set_replay([[4], [4]])
+    eng.reset()
+    eng.run(backend.MODE_REPLAY, 100)
+    with pytest.raises(RuntimeError, match="replay action stream exhausted"):
         eng.check_errors()
     eng.close()
