@@ -55,7 +55,8 @@ static int dev_zero(void *d, size_t n, void *) { memset(d, 0, n); return 0; }
 struct InitArgs { char *state; int n_envs, keep_q, keep_ninter, pad; };
 
 SFL_FN void env_init(const Layout &L, const InitArgs &ia, int env_id, int lane) {
-  Env e = make_env(ia.state + (size_t)env_id * L.env_stride, L);
+  char *base = ia.state + (size_t)env_id * L.env_stride;
+  Env e = make_env(base, L, base, 0);
   for (int t = lane; t < L.T; t += SFL_LANES) { e.prev_port[t] = -1; e.source_port[t] = -1; e.pend_n[t] = 0; }
   if (!ia.keep_ninter) for (int s = lane; s < L.S; s += SFL_LANES) e.ninter[s] = 0;
   if (!ia.keep_q) {
@@ -80,14 +81,18 @@ __global__ void __launch_bounds__(32 * SFL_WARPS_PER_CTA) k_init(Layout L, InitA
 // One warp per environment, SFL_WARPS_PER_CTA environments per CTA; the per-warp exchange block lives in
 // shared memory.  Each warp advances its environment by up to max_ticks flatland ticks and every
 // switch-agent decision in between, resetting the environment in place when an episode ends.
-__global__ void __launch_bounds__(32 * SFL_WARPS_PER_CTA) k_run(DevMap m, Layout L, RunArgs ra, int q_init_on) {
-  __shared__ Scratch sc[SFL_WARPS_PER_CTA];
+// Dynamic shared memory per warp: [hot env state (hot_bytes) | sfl_hparams | Scratch]; the hot state (header, train
+// arrays, pending lists, semaphores when they fit) is staged once per launch and written back at the end, so the
+// tick / decision loops touch HBM only for Q rows, the reward matrix and the interaction counters.
+__global__ void __launch_bounds__(32 * SFL_WARPS_PER_CTA) k_run(DevMap m, Layout L, RunArgs ra, int q_init_on, unsigned hot_bytes, unsigned warp_smem) {
+  extern __shared__ __align__(16) char smem[];
   int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int env_id = blockIdx.x * SFL_WARPS_PER_CTA + w;
   if (env_id >= ra.n_envs) return;
-  if (lane == 0) ((EnvHdr *)(ra.state + (size_t)env_id * L.env_stride))->q_init_on = q_init_on;
-  __syncwarp();
-  env_run(m, L, ra, sc[w], env_id, lane);
+  char *mine = smem + (size_t)w * warp_smem;
+  sfl_hparams *hp_stage = (sfl_hparams *)(mine + hot_bytes);
+  Scratch *sc = (Scratch *)(mine + hot_bytes + ((sizeof(sfl_hparams) + 15) / 16 * 16));
+  env_run(m, L, ra, *sc, env_id, lane, mine, hot_bytes, hp_stage, q_init_on);
 }
 
 __global__ void k_sum(const sfl_env_counters *c, int n, unsigned long long *out) {
@@ -105,6 +110,7 @@ struct Ctx {
   sfl_config cfg;
   sfl_buffers bufs;
   int bound, device, q_init_on;
+  unsigned hot_bytes, warp_smem;
   void *blob;          // device block holding every map table
   void *sum_buf;       // 2 x u64
   std::vector<int32_t> sw_A, port_switch;
@@ -228,10 +234,16 @@ int sfl_create(const sfl_map_desc *map, const sfl_config *cfg, int device, void 
   DevMap &m = c->m;
   m.H = H; m.W = W; m.Hp = Hp; m.Wp = Wp; m.S = S; m.NP = NP; m.NA = NA; m.T = T; m.NT = NT; m.max_episode_steps = map->max_episode_steps;
   m.a_max = a_max; m.pad0 = 0;
-  m.grid = (const uint16_t *)(b + o_grid); m.cell_switch = (const int16_t *)(b + o_csw); m.sw = (const int4 *)(b + o_sw);
-  m.port = (const int4 *)(b + o_port); m.port_switch = (const int16_t *)(b + o_psw); m.act = (const int4 *)(b + o_act);
-  m.train0 = (const int4 *)(b + o_t0); m.train1 = (const int4 *)(b + o_t1); m.init_delay = (const int *)(b + o_idl);
-  m.dist = (const int *)(b + o_dist); m.qinit = (const int8_t *)(b + o_qi);
+  m.grid.p = (const uint16_t *)(b + o_grid); m.cell_switch.p = (const int16_t *)(b + o_csw); m.sw.p = (const int4 *)(b + o_sw);
+  m.port.p = (const int4 *)(b + o_port); m.port_switch.p = (const int16_t *)(b + o_psw); m.act.p = (const int4 *)(b + o_act);
+  m.train0.p = (const int4 *)(b + o_t0); m.train1.p = (const int4 *)(b + o_t1); m.init_delay.p = (const int *)(b + o_idl);
+  m.dist.p = (const int *)(b + o_dist); m.qinit.p = (const int8_t *)(b + o_qi);
+  // hot region: everything up to the reward matrix when the semaphore records fit the per-warp budget, else up to them
+  c->hot_bytes = (L.off_rewards <= 8192u) ? L.off_rewards : L.off_sem;
+  c->warp_smem = c->hot_bytes + (unsigned)((sizeof(sfl_hparams) + 15) / 16 * 16) + (unsigned)((sizeof(Scratch) + 15) / 16 * 16);
+#ifndef SFL_HOST_EMUL
+  CU(cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->warp_smem * SFL_WARPS_PER_CTA)));
+#endif
   *ctx_out = c;
   return SFL_OK;
 }
@@ -300,14 +312,11 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   ra.replay_ev = (mode == SFL_MODE_REPLAY && c->cfg.ev_cap > 0) ? (const int *)c->bufs.replay_ev : nullptr;
 #ifndef SFL_HOST_EMUL
   int grid = (c->cfg.n_envs + SFL_WARPS_PER_CTA - 1) / SFL_WARPS_PER_CTA;
-  k_run<<<grid, 32 * SFL_WARPS_PER_CTA, 0, (cudaStream_t)stream>>>(c->m, c->L, ra, c->q_init_on);
+  k_run<<<grid, 32 * SFL_WARPS_PER_CTA, c->warp_smem * SFL_WARPS_PER_CTA, (cudaStream_t)stream>>>(c->m, c->L, ra, c->q_init_on, c->hot_bytes, c->warp_smem);
   CU(cudaGetLastError());
 #else
   static Scratch sc;
-  for (int i = 0; i < c->cfg.n_envs; i++) {
-    ((EnvHdr *)(ra.state + (size_t)i * c->L.env_stride))->q_init_on = c->q_init_on;
-    env_run(c->m, c->L, ra, sc, i, 0);
-  }
+  for (int i = 0; i < c->cfg.n_envs; i++) env_run(c->m, c->L, ra, sc, i, 0, nullptr, 0, nullptr, c->q_init_on);
 #endif
   return SFL_OK;
 }

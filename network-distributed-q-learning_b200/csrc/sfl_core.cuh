@@ -70,19 +70,29 @@ SFL_FN double dadd(double a, double b) { volatile double r = a + b; return r; }
 #endif
 
 // ------------------------------------------------------------------------------------------------ device views
+// read-only map table: loads go through the non-coherent path (LDG.CONSTANT, L1-resident across the launch)
+template <class T> struct RO {
+  const T *p;
+#if SFL_LANES == 32
+  SFL_FN T operator[](size_t i) const { return __ldg(p + i); }
+#else
+  SFL_FN T operator[](size_t i) const { return p[i]; }
+#endif
+};
+
 struct DevMap {            // map constants (device pointers), passed by value to the kernels
   int H, W, Hp, Wp, S, NP, NA, T, NT, max_episode_steps, a_max, pad0;
-  const uint16_t *grid;        // [Hp*Wp] zero border of 1 cell: moves from a rail cell never leave the array
-  const int16_t *cell_switch;  // [Hp*Wp]
-  const int4 *sw;              // [S]  {P, A, port0, act0}
-  const int4 *port;            // [NP] {nbr, dist, n_intra, intra0}
-  const int16_t *port_switch;  // [NP]
-  const int4 *act;             // [NA] {in_local, out_local, move, 0}
-  const int4 *train0;          // [T]  {init_cell, init_dir, target_cell, tgt_index}   (padded cell ids)
-  const int4 *train1;          // [T]  {ed, la, first_port, first_dist}
-  const int *init_delay;       // [T]
-  const int *dist;             // [NT][Hp*Wp][4]
-  const int8_t *qinit;         // [NP*NT]  -1 | action | final<<4
+  RO<uint16_t> grid;           // [Hp*Wp] zero border of 1 cell: moves from a rail cell never leave the array
+  RO<int16_t> cell_switch;     // [Hp*Wp]
+  RO<int4> sw;                 // [S]  {P, A, port0, act0}
+  RO<int4> port;               // [NP] {nbr, dist, n_intra, intra0}
+  RO<int16_t> port_switch;     // [NP]
+  RO<int4> act;                // [NA] {in_local, out_local, move, 0}
+  RO<int4> train0;             // [T]  {init_cell, init_dir, target_cell, tgt_index}   (padded cell ids)
+  RO<int4> train1;             // [T]  {ed, la, first_port, first_dist}
+  RO<int> init_delay;          // [T]
+  RO<int> dist;                // [NT][Hp*Wp][4]
+  RO<int8_t> qinit;            // [NP*NT]  -1 | action | final<<4
 };
 
 struct Layout {            // byte offsets inside one env block
@@ -115,18 +125,21 @@ struct Env {               // resolved pointers into one env block
   double *q;
 };
 
-SFL_FN Env make_env(char *base, const Layout &L) {
+// `hot` is the staged copy (shared memory on the device) of the first hot_bytes of the env block: header, train
+// arrays, pending lists and -- when they fit the per-warp budget -- the semaphore records.  On the host build hot == base.
+SFL_FN Env make_env(char *base, const Layout &L, char *hot, int sem_hot) {
   Env e;
-  e.h = (EnvHdr *)base;
-  e.pos = (int *)(base + L.off_pos); e.last_delay = (int *)(base + L.off_last_delay);
-  e.malf = (int16_t *)(base + L.off_malf); e.next_port = (int16_t *)(base + L.off_next_port);
-  e.prev_port = (int16_t *)(base + L.off_prev_port); e.source_port = (int16_t *)(base + L.off_source_port);
-  e.act_switch = (int16_t *)(base + L.off_act_switch);
-  e.dir = (uint8_t *)(base + L.off_dir); e.state = (uint8_t *)(base + L.off_state); e.saved = (uint8_t *)(base + L.off_saved);
-  e.prev_act = (uint8_t *)(base + L.off_prev_act); e.plan_len = (uint8_t *)(base + L.off_plan_len);
-  e.plan = (uint8_t *)(base + L.off_plan); e.pend_n = (uint8_t *)(base + L.off_pend_n);
-  e.pend_key = (uint32_t *)(base + L.off_pend_key); e.pend_meta = (uint32_t *)(base + L.off_pend_meta);
-  e.sem = (int4 *)(base + L.off_sem); e.rewards = (int *)(base + L.off_rewards); e.ninter = (int *)(base + L.off_ninter);
+  e.h = (EnvHdr *)hot;
+  e.pos = (int *)(hot + L.off_pos); e.last_delay = (int *)(hot + L.off_last_delay);
+  e.malf = (int16_t *)(hot + L.off_malf); e.next_port = (int16_t *)(hot + L.off_next_port);
+  e.prev_port = (int16_t *)(hot + L.off_prev_port); e.source_port = (int16_t *)(hot + L.off_source_port);
+  e.act_switch = (int16_t *)(hot + L.off_act_switch);
+  e.dir = (uint8_t *)(hot + L.off_dir); e.state = (uint8_t *)(hot + L.off_state); e.saved = (uint8_t *)(hot + L.off_saved);
+  e.prev_act = (uint8_t *)(hot + L.off_prev_act); e.plan_len = (uint8_t *)(hot + L.off_plan_len);
+  e.plan = (uint8_t *)(hot + L.off_plan); e.pend_n = (uint8_t *)(hot + L.off_pend_n);
+  e.pend_key = (uint32_t *)(hot + L.off_pend_key); e.pend_meta = (uint32_t *)(hot + L.off_pend_meta);
+  e.sem = (int4 *)((sem_hot ? hot : base) + L.off_sem);
+  e.rewards = (int *)(base + L.off_rewards); e.ninter = (int *)(base + L.off_ninter);
   e.q = (double *)(base + L.off_q);
   return e;
 }
@@ -370,7 +383,7 @@ SFL_FN void finish_decision(const DevMap &m, const Layout &L, Env &e, const sfl_
 }
 
 // one switch-agent decision: observe (O1-O3) -> act (Q1) -> apply (E2, E3, R1) -> Q-update (Q2, Q3)
-SFL_FN_NOINLINE void decide(const DevMap &m, const Layout &L, Env &e, const sfl_hparams &hp, const RunArgs &ra, int env_id, int t) {
+SFL_FN void decide(const DevMap &m, const Layout &L, Env &e, const sfl_hparams &hp, const RunArgs &ra, int env_id, int t) {
   EnvHdr *h = e.h;
   const int now = h->elapsed;
   const int s = e.act_switch[t];
@@ -737,10 +750,22 @@ SFL_FN void episode_end(const Layout &L, Env &e, const RunArgs &ra, int env_id) 
 }
 
 // ------------------------------------------------------------------------------------------------ the per-env driver
-SFL_FN void env_run(const DevMap &m, const Layout &L, const RunArgs &ra, Scratch &sc, int env_id, int lane) {
-  Env e = make_env(ra.state + (size_t)env_id * L.env_stride, L);
+// `hot`/`hot_bytes`: per-warp staging area for the hot part of the env block (null on the host build);
+// `hp_stage`: per-warp copy of the env's hyper-parameter record.
+SFL_FN void env_run(const DevMap &m, const Layout &L, const RunArgs &ra, Scratch &sc, int env_id, int lane,
+                    char *hot, unsigned hot_bytes, sfl_hparams *hp_stage, int q_init_on) {
+  char *gbase = ra.state + (size_t)env_id * L.env_stride;
+  if (hot) {
+    for (unsigned o = lane * 16u; o < hot_bytes; o += SFL_LANES * 16u) *(int4 *)(hot + o) = *(const int4 *)(gbase + o);
+    for (unsigned o = lane * 4u; o < (unsigned)sizeof(sfl_hparams); o += SFL_LANES * 4u)
+      *(int *)((char *)hp_stage + o) = *(const int *)((const char *)(ra.hp + env_id) + o);
+    w_sync();
+  }
+  Env e = make_env(gbase, L, hot ? hot : gbase, hot_bytes > L.off_sem);
   EnvHdr *h = e.h;
-  const sfl_hparams hp = ra.hp[env_id];
+  const sfl_hparams &hp = hot ? *hp_stage : ra.hp[env_id];
+  if (lane == 0) h->q_init_on = q_init_on;
+  w_sync();
   int budget = ra.max_ticks;
   for (;;) {
     if (h->halted) break;
@@ -777,6 +802,10 @@ SFL_FN void env_run(const DevMap &m, const Layout &L, const RunArgs &ra, Scratch
     c->decisions = h->decisions; c->ticks = h->ticks; c->train_ticks = h->train_ticks; c->episodes = h->episode;
     c->err = h->err; c->q_rows = h->q_rows; c->halted = h->halted; c->n_dec_logged = h->n_dec_logged;
     c->n_tick_logged = h->n_tick_logged; c->n_ep_logged = h->n_ep_logged; c->elapsed = h->elapsed;
+  }
+  if (hot) {
+    w_sync();
+    for (unsigned o = lane * 16u; o < hot_bytes; o += SFL_LANES * 16u) *(int4 *)(gbase + o) = *(const int4 *)(hot + o);
   }
 }
 
