@@ -54,28 +54,28 @@ static int dev_zero(void *d, size_t n, void *) { memset(d, 0, n); return 0; }
 // ------------------------------------------------------------------------------------------------ kernels
 struct InitArgs { char *state; int n_envs, keep_q, keep_ninter, pad; };
 
-SFL_FN void env_init(const Layout &L, const InitArgs &ia, int env_id, int lane) {
-  char *base = ia.state + (size_t)env_id * L.env_stride;
-  Env e = make_env(base, L, base, 0);
-  for (int t = lane; t < L.T; t += SFL_LANES) { e.prev_port[t] = -1; e.source_port[t] = -1; e.pend_n[t] = 0; }
-  if (!ia.keep_ninter) for (int s = lane; s < L.S; s += SFL_LANES) e.ninter[s] = 0;
+SFL_FN void env_init(const InitArgs &ia, int env_id, int lane) {
+  Env e;
+  e.gb = e.hot = e.semb = ia.state + (size_t)env_id * c_L.env_stride;
+  for (int t = lane; t < c_L.T; t += SFL_LANES) { e.prev_port()[t] = -1; e.source_port()[t] = -1; e.pend_n()[t] = 0; }
+  if (!ia.keep_ninter) for (int s = lane; s < c_L.S; s += SFL_LANES) e.ninter()[s] = 0;
   if (!ia.keep_q) {
-    size_t n = (size_t)L.q_cap * L.q_stride;
-    for (size_t i = lane; i < n; i += SFL_LANES) e.q[i] = 0.0;
+    size_t n = (size_t)c_L.q_cap * c_L.q_stride;
+    for (size_t i = lane; i < n; i += SFL_LANES) e.q()[i] = 0.0;
   }
   if (lane == 0) {
-    int q_rows = ia.keep_q ? e.h->q_rows : 0;
+    int q_rows = ia.keep_q ? e.h()->q_rows : 0;
     EnvHdr z;
     memset(&z, 0, sizeof(z));
     z.need_reset = 1; z.pending_fin = -1; z.cur_dec = -1; z.q_rows = q_rows;
-    *e.h = z;
+    *e.h() = z;
   }
 }
 
 #ifndef SFL_HOST_EMUL
-__global__ void __launch_bounds__(32 * SFL_WARPS_PER_CTA) k_init(Layout L, InitArgs ia) {
+__global__ void __launch_bounds__(32 * SFL_WARPS_PER_CTA) k_init(InitArgs ia) {
   int env_id = blockIdx.x * SFL_WARPS_PER_CTA + (threadIdx.x >> 5);
-  if (env_id < ia.n_envs) env_init(L, ia, env_id, threadIdx.x & 31);
+  if (env_id < ia.n_envs) env_init(ia, env_id, threadIdx.x & 31);
 }
 
 // One warp per environment, SFL_WARPS_PER_CTA environments per CTA; the per-warp exchange block lives in
@@ -84,15 +84,15 @@ __global__ void __launch_bounds__(32 * SFL_WARPS_PER_CTA) k_init(Layout L, InitA
 // Dynamic shared memory per warp: [hot env state (hot_bytes) | sfl_hparams | Scratch]; the hot state (header, train
 // arrays, pending lists, semaphores when they fit) is staged once per launch and written back at the end, so the
 // tick / decision loops touch HBM only for Q rows, the reward matrix and the interaction counters.
-__global__ void __launch_bounds__(32 * SFL_WARPS_PER_CTA) k_run(DevMap m, Layout L, RunArgs ra, int q_init_on, unsigned hot_bytes, unsigned warp_smem) {
+__global__ void __launch_bounds__(32 * SFL_WARPS_PER_CTA, 7) k_run(int q_init_on, unsigned hot_bytes, unsigned warp_smem) {
   extern __shared__ __align__(16) char smem[];
   int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int env_id = blockIdx.x * SFL_WARPS_PER_CTA + w;
-  if (env_id >= ra.n_envs) return;
+  if (env_id >= c_ra.n_envs) return;
   char *mine = smem + (size_t)w * warp_smem;
   sfl_hparams *hp_stage = (sfl_hparams *)(mine + hot_bytes);
   Scratch *sc = (Scratch *)(mine + hot_bytes + ((sizeof(sfl_hparams) + 15) / 16 * 16));
-  env_run(m, L, ra, *sc, env_id, lane, mine, hot_bytes, hp_stage, q_init_on);
+  env_run(*sc, env_id, lane, mine, hot_bytes, hp_stage, q_init_on);
 }
 
 __global__ void k_sum(const sfl_env_counters *c, int n, unsigned long long *out) {
@@ -115,6 +115,10 @@ struct Ctx {
   void *sum_buf;       // 2 x u64
   std::vector<int32_t> sw_A, port_switch;
 };
+
+// publish the context's map / layout (and the launch arguments) to constant memory, in stream order
+struct Ctx;
+static int set_constants(const Ctx *c, const RunArgs *ra, void *stream);
 
 static unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 
@@ -145,6 +149,18 @@ static int make_layout(const sfl_map_desc *map, const sfl_config *cfg, Layout *L
   L->env_stride = ((unsigned long long)o + (unsigned long long)cfg->q_cap * L->q_stride * 8ull + 127ull) / 128ull * 128ull;
   *a_max_out = a_max;
   return SFL_OK;
+}
+
+static int set_constants(const Ctx *c, const RunArgs *ra, void *stream) {
+#ifndef SFL_HOST_EMUL
+  if (cudaMemcpyToSymbolAsync(c_m, &c->m, sizeof(DevMap), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbolAsync(c_L, &c->L, sizeof(Layout), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess) return 1;
+  if (ra && cudaMemcpyToSymbolAsync(c_ra, ra, sizeof(RunArgs), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess) return 1;
+#else
+  c_m = c->m; c_L = c->L;
+  if (ra) c_ra = *ra;
+#endif
+  return 0;
 }
 
 extern "C" {
@@ -276,10 +292,12 @@ int sfl_reset(void *ctx, int keep, void *stream) {
   CK(dev_zero(c->bufs.counters, (size_t)c->cfg.n_envs * sizeof(sfl_env_counters), stream));
 #ifndef SFL_HOST_EMUL
   int grid = (c->cfg.n_envs + SFL_WARPS_PER_CTA - 1) / SFL_WARPS_PER_CTA;
-  k_init<<<grid, 32 * SFL_WARPS_PER_CTA, 0, (cudaStream_t)stream>>>(c->L, ia);
+  CK(set_constants(c, nullptr, stream));
+  k_init<<<grid, 32 * SFL_WARPS_PER_CTA, 0, (cudaStream_t)stream>>>(ia);
   CU(cudaGetLastError());
 #else
-  for (int i = 0; i < c->cfg.n_envs; i++) env_init(c->L, ia, i, 0);
+  set_constants(c, nullptr, stream);
+  for (int i = 0; i < c->cfg.n_envs; i++) env_init(ia, i, 0);
 #endif
   return SFL_OK;
 }
@@ -312,11 +330,13 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   ra.replay_ev = (mode == SFL_MODE_REPLAY && c->cfg.ev_cap > 0) ? (const int *)c->bufs.replay_ev : nullptr;
 #ifndef SFL_HOST_EMUL
   int grid = (c->cfg.n_envs + SFL_WARPS_PER_CTA - 1) / SFL_WARPS_PER_CTA;
-  k_run<<<grid, 32 * SFL_WARPS_PER_CTA, c->warp_smem * SFL_WARPS_PER_CTA, (cudaStream_t)stream>>>(c->m, c->L, ra, c->q_init_on, c->hot_bytes, c->warp_smem);
+  CK(set_constants(c, &ra, stream));
+  k_run<<<grid, 32 * SFL_WARPS_PER_CTA, c->warp_smem * SFL_WARPS_PER_CTA, (cudaStream_t)stream>>>(c->q_init_on, c->hot_bytes, c->warp_smem);
   CU(cudaGetLastError());
 #else
   static Scratch sc;
-  for (int i = 0; i < c->cfg.n_envs; i++) env_run(c->m, c->L, ra, sc, i, 0, nullptr, 0, nullptr, c->q_init_on);
+  set_constants(c, &ra, stream);
+  for (int i = 0; i < c->cfg.n_envs; i++) env_run(sc, i, 0, nullptr, 0, nullptr, c->q_init_on);
 #endif
   return SFL_OK;
 }
