@@ -177,7 +177,8 @@ def run_ours(args):
 
     # ---------------- device-resident arm: Engine level, CUDA-event timed
     rm = backend.RailMap(fx)
-    eng = backend.Engine(rm, n_envs=B, device=dev, q_cap=args.q_cap, ep_cap=4)
+    eng = backend.Engine(rm, n_envs=B, device=dev, q_cap=args.q_cap, ep_cap=4, lanes=args.lanes or None)
+    lanes = eng.lanes
     eng.set_hparams(**HP, seeds=seeds, episodes=-1)
     eng.reset()
     eng.enable_q_init(True)
@@ -210,7 +211,8 @@ def run_ours(args):
     torch.cuda.empty_cache()
 
     # ---------------- end-to-end arm: public API, host buffers in the timed region
-    env = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=B, device=dev, q_cap=args.q_cap, ep_cap=4)
+    env = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=B, device=dev, q_cap=args.q_cap, ep_cap=4,
+                             _engine_kwargs={"lanes": args.lanes or None})
     model = api.DistrQLearning(env=env, seed=SEED + rank * B, **HP)
     for _ in range(args.warmup):
         model.learn_chunk(args.ticks)
@@ -258,7 +260,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_envs_per_gpu": B, "ticks_per_step": args.ticks, "q_cap": args.q_cap,
+            "config": {"workload": WORKLOAD, "n_envs_per_gpu": B, "ticks_per_step": args.ticks, "q_cap": args.q_cap, "lanes_per_env": lanes,
                        "train_ticks_per_decision": k_bar, "ticks": ticks,
                        "l2": f"inputs larger than L2: {state_mb:.0f} MB of env state + Q tables per GPU vs 126 MB L2",
                        "sharding": "envs by seed range, no data-path collective"},
@@ -287,6 +289,7 @@ def main():
     ap.add_argument("--envs", type=int, default=N_ENVS, help="environments per GPU")
     ap.add_argument("--ticks", type=int, default=512, help="flatland ticks per env per step (launch)")
     ap.add_argument("--q-cap", type=int, default=1024)
+    ap.add_argument("--lanes", type=int, default=0, help="lanes of a warp per environment (0 = library default for the batch size)")
     ap.add_argument("--cpu-seconds", type=float, default=3.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -82,6 +82,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sfl_bind.argtypes = [C.c_void_p, C.POINTER(Buffers)]
     lib.sfl_reset.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.sfl_enable_q_init.argtypes = [C.c_void_p, C.c_int]
+    lib.sfl_set_lanes.argtypes = [C.c_void_p, C.c_int]
+    lib.sfl_get_lanes.argtypes = [C.c_void_p]
     lib.sfl_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.sfl_total_decisions.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
     lib.sfl_export_q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.c_void_p]
@@ -187,7 +189,7 @@ class Engine:
 
     def __init__(self, rail_map: RailMap, n_envs: int, device: str = "cuda:0", q_cap: int = 1024, pend_cap: int = 8,
                  max_steps: int = 100_000, dec_cap: int = 0, tick_cap: int = 0, ep_cap: int = 64, act_cap: int = 0,
-                 ev_cap: int = 0, trace_sem: bool = False, _emul_lib: Optional[str] = None):
+                 ev_cap: int = 0, trace_sem: bool = False, lanes: Optional[int] = None, _emul_lib: Optional[str] = None):
         import torch
         self.torch = torch
         self.map = rail_map
@@ -217,6 +219,8 @@ class Engine:
                     "replay_ev": z(s.replay_ev_bytes)}
         b = Buffers(**{k: v.data_ptr() for k, v in self.buf.items()})
         self._ck(self.lib.sfl_bind(self.ctx, C.byref(b)))
+        if lanes is not None:
+            self._ck(self.lib.sfl_set_lanes(self.ctx, int(lanes)))
         self.hparams = np.zeros(self.n_envs, HPARAMS_DT)
         self._pinned = {}
 
@@ -278,6 +282,11 @@ class Engine:
 
     def reset(self, keep_q: bool = False, keep_interactions: bool = False):
         self._ck(self.lib.sfl_reset(self.ctx, int(keep_q) | (int(keep_interactions) << 1), self._stream()))
+
+    @property
+    def lanes(self) -> int:
+        """Lanes of a warp cooperating on one environment (a scheduling choice; results do not depend on it)."""
+        return int(self.lib.sfl_get_lanes(self.ctx))
 
     def enable_q_init(self, on: bool = True):
         self._ck(self.lib.sfl_enable_q_init(self.ctx, int(on)))

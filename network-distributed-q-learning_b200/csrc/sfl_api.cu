@@ -50,18 +50,29 @@ static int dev_zero(void *d, size_t n, void *) { memset(d, 0, n); return 0; }
 #endif
 
 #define SFL_WARPS_PER_CTA 4
+#define SFL_CTA_THREADS (32 * SFL_WARPS_PER_CTA)
+#define SFL_SMEM_BUDGET (56u * 1024u)                  // per CTA, so that four CTAs share an SM
 
 // ------------------------------------------------------------------------------------------------ kernels
 struct InitArgs { char *state; int n_envs, keep_q, keep_ninter, pad; };
 
-SFL_FN void env_init(const InitArgs &ia, int env_id, int lane) {
-  Env e;
-  e.gb = e.hot = e.semb = ia.state + (size_t)env_id * c_L.env_stride;
-  for (int t = lane; t < c_L.T; t += SFL_LANES) { e.prev_port()[t] = -1; e.source_port()[t] = -1; e.pend_n()[t] = 0; }
-  if (!ia.keep_ninter) for (int s = lane; s < c_L.S; s += SFL_LANES) e.ninter()[s] = 0;
+struct InitEnv {          // the env block in HBM, no staging
+  char *b;
+  SFL_FN EnvHdr *h() const { return (EnvHdr *)b; }
+  SFL_FN int4 *tra() const { return (int4 *)(b + c_L.off_tra); }
+  SFL_FN int4 *trb() const { return (int4 *)(b + c_L.off_trb); }
+  SFL_FN SwS *sws() const { return (SwS *)(b + c_L.off_sws); }
+  SFL_FN double *q() const { return (double *)(b + c_L.off_q); }
+};
+
+SFL_FN void env_init(const InitArgs &ia, int env_id, int lane, int lanes) {
+  InitEnv e;
+  e.b = ia.state + (size_t)env_id * c_L.env_stride;
+  for (int t = lane; t < c_L.T; t += lanes) { e.tra()[t] = make_int4(-1, 0, 0, 0); e.trb()[t] = make_int4(-1, 0xFFFF, 0, 0); }
+  if (!ia.keep_ninter) for (int s = lane; s < c_L.S; s += lanes) { SwS z; z.ninter = 0; z.pad = 0; z.eps_pow = 1.0; e.sws()[s] = z; }
   if (!ia.keep_q) {
     size_t n = (size_t)c_L.q_cap * c_L.q_stride;
-    for (size_t i = lane; i < n; i += SFL_LANES) e.q()[i] = 0.0;
+    for (size_t i = lane; i < n; i += lanes) e.q()[i] = 0.0;
   }
   if (lane == 0) {
     int q_rows = ia.keep_q ? e.h()->q_rows : 0;
@@ -73,26 +84,21 @@ SFL_FN void env_init(const InitArgs &ia, int env_id, int lane) {
 }
 
 #ifndef SFL_HOST_EMUL
-__global__ void __launch_bounds__(32 * SFL_WARPS_PER_CTA) k_init(InitArgs ia) {
+__global__ void __launch_bounds__(SFL_CTA_THREADS) k_init(InitArgs ia) {
   int env_id = blockIdx.x * SFL_WARPS_PER_CTA + (threadIdx.x >> 5);
-  if (env_id < ia.n_envs) env_init(ia, env_id, threadIdx.x & 31);
+  if (env_id < ia.n_envs) env_init(ia, env_id, threadIdx.x & 31, 32);
 }
 
-// One warp per environment, SFL_WARPS_PER_CTA environments per CTA; the per-warp exchange block lives in
-// shared memory.  Each warp advances its environment by up to max_ticks flatland ticks and every
-// switch-agent decision in between, resetting the environment in place when an episode ends.
-// Dynamic shared memory per warp: [hot env state (hot_bytes) | sfl_hparams | Scratch]; the hot state (header, train
-// arrays, pending lists, semaphores when they fit) is staged once per launch and written back at the end, so the
-// tick / decision loops touch HBM only for Q rows, the reward matrix and the interaction counters.
-__global__ void __launch_bounds__(32 * SFL_WARPS_PER_CTA, 7) k_run(int q_init_on, unsigned hot_bytes, unsigned warp_smem) {
-  extern __shared__ __align__(16) char smem[];
-  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int env_id = blockIdx.x * SFL_WARPS_PER_CTA + w;
-  if (env_id >= c_ra.n_envs) return;
-  char *mine = smem + (size_t)w * warp_smem;
-  sfl_hparams *hp_stage = (sfl_hparams *)(mine + hot_bytes);
-  Scratch *sc = (Scratch *)(mine + hot_bytes + ((sizeof(sfl_hparams) + 15) / 16 * 16));
-  env_run(*sc, env_id, lane, mine, hot_bytes, hp_stage, q_init_on);
+// G lanes per environment, 32/G environments per warp, SFL_WARPS_PER_CTA warps per CTA.  Dynamic shared memory per
+// environment: [hot env state (hot_bytes) | sfl_hparams | Scratch]; the hot state (header, train records, pending
+// lists and -- when they fit -- semaphores, rewards and per-switch counters) is staged once per launch and written
+// back at the end, so the tick / decision loops touch HBM only for Q rows.
+template <int G, bool TRACE, bool TH>
+__global__ void __launch_bounds__(SFL_CTA_THREADS, G == 32 ? 7 : 4) k_run() {
+  const int slot = threadIdx.x / G;                    // environment slot inside the CTA
+  const int env_id = blockIdx.x * (blockDim.x / G) + slot;
+  if (env_id >= c_ra.n_envs) return;                   // whole groups leave together
+  env_run<G, TRACE, TH>(env_id, (unsigned)slot * c_ra.env_smem, nullptr);
 }
 
 __global__ void k_sum(const sfl_env_counters *c, int n, unsigned long long *out) {
@@ -100,6 +106,22 @@ __global__ void k_sum(const sfl_env_counters *c, int n, unsigned long long *out)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { d += c[i].decisions; t += c[i].ticks; }
   for (int o = 16; o; o >>= 1) { d += __shfl_down_sync(0xffffffffu, d, o); t += __shfl_down_sync(0xffffffffu, t, o); }
   if ((threadIdx.x & 31) == 0) { atomicAdd(out, d); atomicAdd(out + 1, t); }
+}
+
+typedef void (*run_kernel_t)();
+template <int G> static run_kernel_t pick_kernel_g(int trace, int th) {
+  if (trace) return th ? k_run<G, true, true> : k_run<G, true, false>;
+  return th ? k_run<G, false, true> : k_run<G, false, false>;
+}
+static run_kernel_t pick_kernel(int G, int trace, int th) {
+  switch (G) {
+    case 1: return pick_kernel_g<1>(trace, th);
+    case 2: return pick_kernel_g<2>(trace, th);
+    case 4: return pick_kernel_g<4>(trace, th);
+    case 8: return pick_kernel_g<8>(trace, th);
+    case 16: return pick_kernel_g<16>(trace, th);
+    default: return pick_kernel_g<32>(trace, th);
+  }
 }
 #endif
 
@@ -109,16 +131,25 @@ struct Ctx {
   Layout L;
   sfl_config cfg;
   sfl_buffers bufs;
-  int bound, device, q_init_on;
-  unsigned hot_bytes, warp_smem;
+  int bound, device, q_init_on, lanes, sm_count;
+  unsigned hot_bytes, env_smem, tail_hot;
   void *blob;          // device block holding every map table
   void *sum_buf;       // 2 x u64
-  std::vector<int32_t> sw_A, port_switch;
 };
 
-// publish the context's map / layout (and the launch arguments) to constant memory, in stream order
-struct Ctx;
 static int set_constants(const Ctx *c, const RunArgs *ra, void *stream);
+
+// Shared-memory staging plan for c->lanes lanes per environment: the whole non-Q state (header, train records, pending
+// lists, semaphores, rewards, per-switch counters) when that still leaves room for 16 warps per SM,
+// else only header + train records + pending lists (semaphores, rewards and counters then stay in HBM / L2).
+static int choose_hot(Ctx *c) {
+  const unsigned fixed = (unsigned)sizeof(sfl_hparams) + scratch_bytes(c->L.T);
+  const unsigned per_warp = 32u / (unsigned)c->lanes;
+  if ((size_t)(c->L.off_q + fixed) * per_warp <= 14u * 1024u) { c->tail_hot = 1; c->hot_bytes = c->L.off_q; }   // >= 16 warps per SM
+  else { c->tail_hot = 0; c->hot_bytes = c->L.off_sem; }
+  c->env_smem = c->hot_bytes + fixed;
+  return (size_t)c->env_smem * per_warp > 227u * 1024u;
+}
 
 static unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 
@@ -127,6 +158,7 @@ static int make_layout(const sfl_map_desc *map, const sfl_config *cfg, Layout *L
   if (map->T < 1 || map->T > SFL_MAX_T) return fail(SFL_E_ARG, "T must be in 1..64%s");
   if (map->S < 1 || map->S > 4095) return fail(SFL_E_ARG, "S must be in 1..4095%s");
   if (map->NP > 32767) return fail(SFL_E_ARG, "too many ports%s");
+  if ((int64_t)(map->H + 2) * (map->W + 2) >= (1 << 28)) return fail(SFL_E_ARG, "grid too large%s");
   if (cfg->q_cap < 2 || (cfg->q_cap & (cfg->q_cap - 1))) return fail(SFL_E_ARG, "q_cap must be a power of two%s");
   if (cfg->pend_cap < 1 || cfg->pend_cap > 64 || cfg->n_envs < 1) return fail(SFL_E_ARG, "bad pend_cap / n_envs%s");
   int a_max = 0;
@@ -139,11 +171,8 @@ static int make_layout(const sfl_map_desc *map, const sfl_config *cfg, Layout *L
   unsigned o = align_up((unsigned)sizeof(EnvHdr), 16);
   unsigned T = (unsigned)map->T;
 #define PUT(field, bytes) L->field = o; o = align_up(o + (unsigned)(bytes), 16)
-  PUT(off_pos, 4 * T); PUT(off_last_delay, 4 * T);
-  PUT(off_malf, 2 * T); PUT(off_next_port, 2 * T); PUT(off_prev_port, 2 * T); PUT(off_source_port, 2 * T); PUT(off_act_switch, 2 * T);
-  PUT(off_dir, T); PUT(off_state, T); PUT(off_saved, T); PUT(off_prev_act, T); PUT(off_plan_len, T); PUT(off_plan, SFL_PLAN_CAP * T); PUT(off_pend_n, T);
-  PUT(off_pend_key, 4 * T * cfg->pend_cap); PUT(off_pend_meta, 4 * T * cfg->pend_cap);
-  PUT(off_sem, 16 * (unsigned)map->NP); PUT(off_rewards, 4 * (unsigned)map->S * T); PUT(off_ninter, 4 * (unsigned)map->S);
+  PUT(off_tra, 16 * T); PUT(off_trb, 16 * T); PUT(off_pend, 8 * T * cfg->pend_cap);
+  PUT(off_sem, 16 * (unsigned)map->NP); PUT(off_rewards, 4 * (unsigned)map->S * T); PUT(off_sws, 16 * (unsigned)map->S);
 #undef PUT
   L->off_q = o;
   L->env_stride = ((unsigned long long)o + (unsigned long long)cfg->q_cap * L->q_stride * 8ull + 127ull) / 128ull * 128ull;
@@ -190,43 +219,79 @@ int sfl_query_sizes(const sfl_map_desc *map, const sfl_config *cfg, sfl_sizes *o
   return SFL_OK;
 }
 
+// flatland rail.check_action_on_agent for every (cell, heading, action), SURVEY.md Appendix B (row F1)
+static uint16_t move_entry(unsigned v, int dir) {
+  if (!v) return 0;
+  unsigned nib = (v >> ((3 - dir) * 4)) & 0xFu;
+  int n = __builtin_popcount(nib);
+  uint16_t e = 0x8000u;
+  for (int a = 0; a <= 4; a++) {
+    int nd = dir, valid = -1;
+    if (a == A_LEFT) { nd = dir - 1; if (n <= 1) valid = 0; }
+    else if (a == A_RIGHT) { nd = dir + 1; if (n <= 1) valid = 0; }
+    nd &= 3;
+    if (a == A_FWD && n == 1) { nd = 3 - (31 - __builtin_clz(nib)); valid = 1; }
+    if (valid < 0) valid = (nib >> (3 - nd)) & 1;
+    e |= (uint16_t)((valid | (nd << 1)) << (3 * a));
+  }
+  return e;
+}
+
 int sfl_create(const sfl_map_desc *map, const sfl_config *cfg, int device, void **ctx_out) {
   if (!ctx_out) return fail(SFL_E_ARG, "null ctx%s");
   Layout L; int a_max;
   int rc = make_layout(map, cfg, &L, &a_max);
   if (rc) return rc;
+  const int H = map->H, W = map->W, Hp = H + 2, Wp = W + 2, T = map->T, NT = map->NT, S = map->S, NP = map->NP, NA = map->NA;
+  // every transition must lead to a rail cell inside the grid (flatland maps are consistent); the device relies on it
+  for (int r = 0; r < H; r++) for (int cc = 0; cc < W; cc++) {
+    unsigned v = map->grid[r * W + cc];
+    for (int x = 0; x < 4; x++) {
+      if (!(((v >> 12) | (v >> 8) | (v >> 4) | v) & (8u >> x))) continue;
+      int nr = r + (x == 0 ? -1 : x == 2 ? 1 : 0), nc = cc + (x == 1 ? 1 : x == 3 ? -1 : 0);
+      if (nr < 0 || nr >= H || nc < 0 || nc >= W || !map->grid[nr * W + nc]) return fail(SFL_E_ARG, "inconsistent map: a transition leads off the rails%s");
+    }
+  }
+  int sm_count = 148;
 #ifndef SFL_HOST_EMUL
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(SFL_E_CUDA, "no CUDA device: this library has no CPU path%s");
   CU(cudaSetDevice(device));
+  CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
 #endif
   Ctx *c = new (std::nothrow) Ctx();
   if (!c) return fail(SFL_E_NOMEM, "host alloc%s");
-  c->L = L; c->cfg = *cfg; c->bound = 0; c->device = device; c->q_init_on = 0; c->blob = nullptr; c->sum_buf = nullptr;
+  c->L = L; c->cfg = *cfg; c->bound = 0; c->device = device; c->q_init_on = 0; c->blob = nullptr; c->sum_buf = nullptr; c->sm_count = sm_count;
   memset(&c->bufs, 0, sizeof(c->bufs));
-  const int H = map->H, W = map->W, Hp = H + 2, Wp = W + 2, T = map->T, NT = map->NT, S = map->S, NP = map->NP, NA = map->NA;
   auto pcell = [&](int cell) { return cell < 0 ? -1 : (cell / W + 1) * Wp + (cell % W + 1); };
   // ---- pack every table into one host image, 16-byte aligned sections
   std::vector<unsigned char> img;
   auto section = [&](size_t bytes) { size_t o = (img.size() + 15) / 16 * 16; img.resize(o + bytes, 0); return o; };
-  size_t o_grid = section(2ull * Hp * Wp), o_csw = section(2ull * Hp * Wp), o_sw = section(16ull * S), o_port = section(16ull * NP);
-  size_t o_psw = section(2ull * NP), o_act = section(16ull * (NA ? NA : 1)), o_t0 = section(16ull * T), o_t1 = section(16ull * T);
+  size_t o_move = section(8ull * Hp * Wp), o_csw = section(2ull * Hp * Wp), o_sw = section(16ull * S), o_port = section(16ull * NP);
+  size_t o_pexit = section(16ull * NP), o_act = section(16ull * (NA ? NA : 1)), o_t0 = section(16ull * T), o_t1 = section(16ull * T);
   size_t o_idl = section(4ull * T), o_dist = section(16ull * NT * Hp * Wp), o_qi = section((size_t)NP * NT);
-  uint16_t *grid = (uint16_t *)&img[o_grid]; int16_t *csw = (int16_t *)&img[o_csw];
+  uint16_t *move = (uint16_t *)&img[o_move]; int16_t *csw = (int16_t *)&img[o_csw];
   for (int i = 0; i < Hp * Wp; i++) csw[i] = -1;
   for (int r = 0; r < H; r++) for (int cc = 0; cc < W; cc++) {
-    grid[(r + 1) * Wp + cc + 1] = map->grid[r * W + cc];
-    csw[(r + 1) * Wp + cc + 1] = (int16_t)map->cell_switch[r * W + cc];
+    int pc = (r + 1) * Wp + cc + 1;
+    for (int d = 0; d < 4; d++) move[pc * 4 + d] = move_entry(map->grid[r * W + cc], d);
+    csw[pc] = (int16_t)map->cell_switch[r * W + cc];
   }
   int4 *sw = (int4 *)&img[o_sw];
-  c->sw_A.assign(map->sw_A, map->sw_A + S);
   for (int s = 0; s < S; s++) sw[s] = make_int4(map->sw_P[s], map->sw_A[s], map->sw_port0[s], map->sw_act0[s]);
-  int4 *port = (int4 *)&img[o_port]; int16_t *psw = (int16_t *)&img[o_psw];
-  for (int p = 0; p < NP; p++) port[p] = make_int4(map->port_nbr[p], map->port_dist[p], map->port_n_intra[p], map->port_intra0[p]);
-  for (int s = 0; s < S; s++) for (int p = map->sw_port0[s]; p < map->sw_port0[s + 1]; p++) psw[p] = (int16_t)s;
-  c->port_switch.assign(NP, 0);
-  for (int p = 0; p < NP; p++) c->port_switch[p] = psw[p];
+  int4 *port = (int4 *)&img[o_port], *pexit = (int4 *)&img[o_pexit];
+  for (int s = 0; s < S; s++)
+    for (int p = map->sw_port0[s]; p < map->sw_port0[s + 1]; p++) {
+      port[p] = make_int4(map->port_nbr[p], map->port_dist[p], map->port_n_intra[p] == 1 ? map->port_intra0[p] : -1, s);
+      int ex[3] = {0, 0, 0}, n = 0;
+      for (int a = map->sw_act0[s]; a < map->sw_act0[s + 1]; a++)
+        if (map->sw_port0[s] + map->act_in[a] == p) {
+          if (n >= 3) { delete c; return fail(SFL_E_ARG, "more than 3 exits from one port%s"); }
+          ex[n++] = (a - map->sw_act0[s]) | (map->act_out[a] << 4) | (map->act_move[a] << 8);
+        }
+      pexit[p] = make_int4(n, ex[0], ex[1], ex[2]);
+    }
   int4 *act = (int4 *)&img[o_act];
   for (int a = 0; a < NA; a++) act[a] = make_int4(map->act_in[a], map->act_out[a], map->act_move[a], 0);
   int4 *t0 = (int4 *)&img[o_t0], *t1 = (int4 *)&img[o_t1]; int *idl = (int *)&img[o_idl];
@@ -250,16 +315,24 @@ int sfl_create(const sfl_map_desc *map, const sfl_config *cfg, int device, void 
   DevMap &m = c->m;
   m.H = H; m.W = W; m.Hp = Hp; m.Wp = Wp; m.S = S; m.NP = NP; m.NA = NA; m.T = T; m.NT = NT; m.max_episode_steps = map->max_episode_steps;
   m.a_max = a_max; m.pad0 = 0;
-  m.grid.p = (const uint16_t *)(b + o_grid); m.cell_switch.p = (const int16_t *)(b + o_csw); m.sw.p = (const int4 *)(b + o_sw);
-  m.port.p = (const int4 *)(b + o_port); m.port_switch.p = (const int16_t *)(b + o_psw); m.act.p = (const int4 *)(b + o_act);
+  m.move.p = (const uint16_t *)(b + o_move); m.cell_switch.p = (const int16_t *)(b + o_csw); m.sw.p = (const int4 *)(b + o_sw);
+  m.port.p = (const int4 *)(b + o_port); m.pexit.p = (const int4 *)(b + o_pexit); m.act.p = (const int4 *)(b + o_act);
   m.train0.p = (const int4 *)(b + o_t0); m.train1.p = (const int4 *)(b + o_t1); m.init_delay.p = (const int *)(b + o_idl);
   m.dist.p = (const int *)(b + o_dist); m.qinit.p = (const int8_t *)(b + o_qi);
-  // hot region: everything up to the reward matrix when the semaphore records fit the per-warp budget, else up to them
-  c->hot_bytes = (L.off_rewards <= 8192u) ? L.off_rewards : L.off_sem;
-  c->warp_smem = c->hot_bytes + (unsigned)((sizeof(sfl_hparams) + 15) / 16 * 16) + (unsigned)((sizeof(Scratch) + 15) / 16 * 16);
-#ifndef SFL_HOST_EMUL
-  CU(cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->warp_smem * SFL_WARPS_PER_CTA)));
-#endif
+  c->lanes = 32;
+  choose_hot(c);
+  // lanes per environment: as few as keep every scheduler of the GPU busy (>= 8 warps each), at least 1
+  {
+    long warps_wanted = (long)sm_count * 4 * 8;
+    int G = 32;
+    while (G > 1 && (long)cfg->n_envs * (G / 2) / 32 >= warps_wanted) {
+      c->lanes = G / 2;
+      if (choose_hot(c)) break;
+      G /= 2;
+    }
+    c->lanes = G;
+    choose_hot(c);
+  }
   *ctx_out = c;
   return SFL_OK;
 }
@@ -284,6 +357,21 @@ int sfl_bind(void *ctx, const sfl_buffers *bufs) {
   return SFL_OK;
 }
 
+int sfl_set_lanes(void *ctx, int lanes) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c) return fail(SFL_E_ARG, "null ctx%s");
+  if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(SFL_E_ARG, "lanes must be 1, 2, 4, 8, 16 or 32%s");
+  int old = c->lanes;
+  c->lanes = lanes;
+  if (choose_hot(c)) { c->lanes = old; choose_hot(c); return fail(SFL_E_ARG, "one warp of environments does not fit shared memory with this few lanes per env%s"); }
+  return SFL_OK;
+}
+
+int sfl_get_lanes(void *ctx) {
+  Ctx *c = (Ctx *)ctx;
+  return c ? c->lanes : SFL_E_ARG;
+}
+
 int sfl_reset(void *ctx, int keep, void *stream) {
   Ctx *c = (Ctx *)ctx;
   if (!c) return fail(SFL_E_ARG, "null ctx%s");
@@ -293,11 +381,11 @@ int sfl_reset(void *ctx, int keep, void *stream) {
 #ifndef SFL_HOST_EMUL
   int grid = (c->cfg.n_envs + SFL_WARPS_PER_CTA - 1) / SFL_WARPS_PER_CTA;
   CK(set_constants(c, nullptr, stream));
-  k_init<<<grid, 32 * SFL_WARPS_PER_CTA, 0, (cudaStream_t)stream>>>(ia);
+  k_init<<<grid, SFL_CTA_THREADS, 0, (cudaStream_t)stream>>>(ia);
   CU(cudaGetLastError());
 #else
   set_constants(c, nullptr, stream);
-  for (int i = 0; i < c->cfg.n_envs; i++) env_init(ia, i, 0);
+  for (int i = 0; i < c->cfg.n_envs; i++) env_init(ia, i, 0, 1);
 #endif
   return SFL_OK;
 }
@@ -319,7 +407,8 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   memset(&ra, 0, sizeof(ra));
   ra.mode = mode; ra.max_ticks = max_ticks; ra.n_envs = c->cfg.n_envs; ra.trace_sem = c->cfg.trace_sem;
   ra.dec_cap = c->cfg.dec_cap; ra.tick_cap = c->cfg.tick_cap; ra.ep_cap = c->cfg.ep_cap; ra.act_cap = c->cfg.act_cap;
-  ra.ev_cap = c->cfg.ev_cap; ra.max_steps = c->cfg.max_steps;
+  ra.ev_cap = c->cfg.ev_cap; ra.max_steps = c->cfg.max_steps; ra.q_init_on = c->q_init_on;
+  ra.hot_bytes = c->hot_bytes; ra.env_smem = c->env_smem; ra.tail_hot = c->tail_hot;
   ra.state = (char *)c->bufs.state; ra.hp = (const sfl_hparams *)c->bufs.hparams; ra.counters = (sfl_env_counters *)c->bufs.counters;
   ra.trace_dec = c->cfg.dec_cap > 0 ? (sfl_dec_rec *)c->bufs.trace_dec : nullptr;
   ra.trace_tick = c->cfg.tick_cap > 0 ? (sfl_tick_rec *)c->bufs.trace_tick : nullptr;
@@ -328,15 +417,26 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   ra.ep_delay = c->cfg.ep_cap > 0 ? (int *)c->bufs.ep_delay : nullptr;
   ra.replay_act = (const int8_t *)c->bufs.replay_act;
   ra.replay_ev = (mode == SFL_MODE_REPLAY && c->cfg.ev_cap > 0) ? (const int *)c->bufs.replay_ev : nullptr;
+  const int trace = ra.trace_dec || ra.trace_tick;
 #ifndef SFL_HOST_EMUL
-  int grid = (c->cfg.n_envs + SFL_WARPS_PER_CTA - 1) / SFL_WARPS_PER_CTA;
+  const int G = c->lanes;
+  int threads = SFL_CTA_THREADS;                       // shrink the CTA until its environments fit shared memory
+  while (threads > 32 && (size_t)c->env_smem * (threads / G) > SFL_SMEM_BUDGET) threads /= 2;
+  const int envs_per_cta = threads / G;
+  const size_t smem = (size_t)c->env_smem * envs_per_cta;
+  if (smem > 227u * 1024u) return fail(SFL_E_ARG, "environment state does not fit shared memory with this many lanes per env: use more lanes%s");
+  int grid = (c->cfg.n_envs + envs_per_cta - 1) / envs_per_cta;
+  run_kernel_t k = pick_kernel(G, trace, (int)c->tail_hot);
+  CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(set_constants(c, &ra, stream));
-  k_run<<<grid, 32 * SFL_WARPS_PER_CTA, c->warp_smem * SFL_WARPS_PER_CTA, (cudaStream_t)stream>>>(c->q_init_on, c->hot_bytes, c->warp_smem);
+  k<<<grid, threads, smem, (cudaStream_t)stream>>>();
   CU(cudaGetLastError());
 #else
-  static Scratch sc;
+  static char host_scratch[16 * SFL_MAX_T + 64 + 4 * SFL_MAX_T + 64];
   set_constants(c, &ra, stream);
-  for (int i = 0; i < c->cfg.n_envs; i++) env_run(sc, i, 0, nullptr, 0, nullptr, c->q_init_on);
+  for (int i = 0; i < c->cfg.n_envs; i++) {
+    if (trace) env_run<1, true, true>(i, 0u, host_scratch); else env_run<1, false, true>(i, 0u, host_scratch);
+  }
 #endif
   return SFL_OK;
 }

@@ -1,0 +1,6 @@
+#!/bin/bash
+# usage: scripts/gpu_profile.sh <tag> [bench args...]   -- plain run first, then launch list + one full ncu capture of k_run
+tag=$1; shift
+python bench.py --steps 2 --warmup 3 --no-cpu "$@" > gpurun_out/plain_$tag.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_run -s 3 -c 1 -o gpurun_out/prof_$tag python bench.py --steps 2 --warmup 3 --no-cpu "$@" > gpurun_out/ncu_$tag.log 2>&1
+tail -1 gpurun_out/plain_$tag.log | cut -c1-300

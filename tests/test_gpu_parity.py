@@ -18,6 +18,13 @@ def test_cuda_replay_matches_reference(name):
     check_replay(name, gpu_engine, n_envs=3)
 
 
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
+@pytest.mark.parametrize("name", ["slips24_t6", "synth40_t12"])
+def test_cuda_replay_any_lane_group_width(name, lanes):
+    """The lanes-per-environment choice is scheduling only: every width reproduces the reference trace."""
+    check_replay(name, lambda rm, **kw: gpu_engine(rm, lanes=lanes, **kw), n_envs=5)
+
+
 def test_cuda_chunked_launches_equal_one_launch():
     check_replay("slips24_t6", gpu_engine, n_envs=2, chunk=5)
 
