@@ -34,9 +34,25 @@ from __graft_entry__ import load_package  # noqa: E402
 METRIC = "switch_agent_decisions_per_sec"
 HP = dict(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0)   # test_model.py:56-63
 SEED = 450565
+# workload -> (fixture, envs per GPU, Q hash rows per env, description)
+WORKLOADS = {
+    "c2": ("c1_synth18", 4096, 1024,
+           "C2: 4096 lockstep envs of the test_model.py map (c1_synth18 stand-in), distributed Q-learning, learn mode"),
+    "c4": ("c4_synth100_t50", 8192, 8192,
+           "C4: large synthetic map (100x100, 50 trains, 281 switches, malfunctions), 65536 envs per 8 GPUs = 8192 per GPU, "
+           "distributed Q-learning, learn mode"),
+}
 FIXTURE = os.path.join(ROOT, "tests", "golden", "c1_synth18.fixture.npz")
-N_ENVS = 4096
-WORKLOAD = "C2: 4096 lockstep envs of the test_model.py map (c1_synth18 stand-in), distributed Q-learning, learn mode"
+WORKLOAD = WORKLOADS["c2"][3]
+
+
+def select_workload(args):
+    global FIXTURE, WORKLOAD
+    name, envs, q_cap, desc = WORKLOADS[args.workload]
+    FIXTURE = os.path.join(ROOT, "tests", "golden", name + ".fixture.npz")
+    WORKLOAD = desc if not args.envs or args.envs == envs else desc + f" [envs per GPU overridden: {args.envs}]"
+    args.envs = args.envs or envs
+    args.q_cap = args.q_cap or q_cap
 
 
 def bytes_per_decision(k_bar: float, P: float, A: float, A2: float) -> float:
@@ -46,18 +62,25 @@ def bytes_per_decision(k_bar: float, P: float, A: float, A2: float) -> float:
 
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    """nvidia-smi sampled every 20 ms from before the warm-up until the end of the e2e arm; the median SM clock is taken
+    over the samples that fall inside the device-timed region when there are any, else over all samples under load."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.window = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
+    def mark(self, t0, t1):
+        self.window = (t0, t1)
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -68,28 +91,39 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, sm_in, mx, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
+                clk, cmax = float(parts[1]), float(parts[2])
             except ValueError:
                 continue
-            for n, v in zip(names, parts[3:7]):
+            sm.append(clk); mx.append(cmax)
+            try:
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if self.window and self.window[0] <= ts <= self.window[1]:
+                    sm_in.append(clk)
+            except ValueError:
+                pass
+            for n, v in zip(names, parts[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         os.unlink(self.f.name)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            use = sm_in if sm_in else sm
+            out.update(sm_mhz=float(np.median(use)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       samples_in_timed_region=len(sm_in))
         return out
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
 def _cpu_worker(args):
-    seed, budget_s, n_ep = args
+    seed, budget_s, n_ep, fixture = args
+    global FIXTURE
+    FIXTURE = fixture
     load_package()
     from switchfl_b200 import backend, mapgen
     from oracle.switchfl_oracle import SwitchFLOracle
@@ -117,7 +151,7 @@ def cpu_sample(budget_s: float, cores: int, n_ep: int = 0, seed0: int = SEED):
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(seed0 + i, budget_s, n_ep) for i in range(cores)])
+        res = pool.map(_cpu_worker, [(seed0 + i, budget_s, n_ep, FIXTURE) for i in range(cores)])
     wall = time.perf_counter() - t0
     dec = sum(r[0] for r in res)
     busy = max(r[1] for r in res)
@@ -138,7 +172,7 @@ def run_reference_arm(args):
         dec += d
         busy += b
     value = dec / busy
-    sample = f"{cores} processes x {per_step_s:.0f} s of oracle learn() episodes per step on c1_synth18, one seed per process"
+    sample = f"{cores} processes x {per_step_s:.0f} s of oracle learn() episodes per step on {os.path.basename(FIXTURE)}, one seed per process"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * busy / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -182,14 +216,15 @@ def run_ours(args):
     eng.set_hparams(**HP, seeds=seeds, episodes=-1)
     eng.reset()
     eng.enable_q_init(True)
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         eng.run(backend.MODE_LEARN, args.ticks)
     barrier()
     d0, t0 = eng.total_decisions()
     tt0 = int(eng.counters()["train_ticks"].sum())
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
+    wall0 = time.time()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for a, b in evs:
@@ -198,12 +233,17 @@ def run_ours(args):
         b.record()
     stop.record()
     barrier()
-    clocks = sampler.stop() if sampler else None
+    if sampler:
+        sampler.mark(wall0, time.time())
     ms = start.elapsed_time(stop)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     d1, t1 = eng.total_decisions()
     tt1 = int(eng.counters()["train_ticks"].sum())
-    eng.check_errors()
+    # On congested maps the reference itself dies in observer.py:294-307 ("No train detected at active switch");
+    # the kernel abandons such an episode and resets the env.  Every other error bit is fatal here.
+    eng.check_errors(allow=backend.ERR_NO_TRAIN_AT_SWITCH)
+    cn = eng.counters()
+    episodes, aborted = int(cn["episodes"].sum()), int(cn["aborted"].sum())
     dec, ticks, train_ticks = d1 - d0, t1 - t0, tt1 - tt0
     state_mb = eng.sizes.state_bytes / 1e6
     eng.close()
@@ -225,6 +265,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - w0
     e2e_dec = int(c["decisions"].sum() - c0)
+    clocks = sampler.stop() if sampler else None
     h2d = int(env.engine.sizes.hparams_bytes)
     d2h = int(env.engine.sizes.counters_bytes)
 
@@ -261,7 +302,8 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_envs_per_gpu": B, "ticks_per_step": args.ticks, "q_cap": args.q_cap, "lanes_per_env": lanes,
-                       "train_ticks_per_decision": k_bar, "ticks": ticks,
+                       "train_ticks_per_decision": k_bar, "ticks": ticks, "episodes_rank0": episodes,
+                       "episodes_abandoned_rank0": aborted,
                        "l2": f"inputs larger than L2: {state_mb:.0f} MB of env state + Q tables per GPU vs 126 MB L2",
                        "sharding": "envs by seed range, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -283,16 +325,18 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=N_ENVS, help="environments per GPU")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = BASELINE.json configs[1] (default), c4 = configs[3]")
+    ap.add_argument("--envs", type=int, default=0, help="environments per GPU (0 = the workload's own)")
     ap.add_argument("--ticks", type=int, default=512, help="flatland ticks per env per step (launch)")
-    ap.add_argument("--q-cap", type=int, default=1024)
+    ap.add_argument("--q-cap", type=int, default=0, help="Q hash rows per environment (0 = the workload's own)")
     ap.add_argument("--lanes", type=int, default=0, help="lanes of a warp per environment (0 = library default for the batch size)")
     ap.add_argument("--cpu-seconds", type=float, default=3.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    select_workload(args)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SFL_ABI_VERSION 1
+#define SFL_ABI_VERSION 2
 
 enum {
   SFL_OK = 0,
@@ -33,7 +33,8 @@ enum {
 
 /* per-environment error bits, reported in sfl_env_counters.err (the reference raises instead)       */
 enum {
-  SFL_ERR_NO_TRAIN_AT_SWITCH = 1,   /* observer.py:294-307                                          */
+  SFL_ERR_NO_TRAIN_AT_SWITCH = 1,   /* observer.py:294-307: the reference logs "Bug detected" and then dies on an unbound
+                                       local (:307); here the episode is abandoned (counted in `aborted`) and the env resets */
   SFL_ERR_INF_DISTANCE = 2,         /* observer.py:35-36  ValueError                                 */
   SFL_ERR_Q_FULL = 4,               /* per-env Q hash table full                                     */
   SFL_ERR_PEND_FULL = 8,            /* pending-update list of a train full (distr_q.py:340-342)      */
@@ -115,6 +116,7 @@ typedef struct sfl_env_counters {      /* written by sfl_run for every env      
   uint64_t decisions, ticks, train_ticks;   /* lifetime totals                                        */
   int32_t episodes, err, q_rows, halted;
   int32_t n_dec_logged, n_tick_logged, n_ep_logged, elapsed;
+  int32_t aborted, reserved;                /* episodes abandoned on SFL_ERR_NO_TRAIN_AT_SWITCH      */
 } sfl_env_counters;
 
 typedef struct sfl_dec_rec {           /* one switch-agent decision (trace)                           */

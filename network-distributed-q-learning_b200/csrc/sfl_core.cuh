@@ -116,7 +116,7 @@ struct EnvHdr {            // 128 bytes at the start of every env block
   int terminated, truncated, need_reset, halted;
   int err, q_rows, pending_fin, cur_dec;
   int act_cursor, ev_cursor, n_dec_logged, n_tick_logged;
-  int n_ep_logged, q_init_on, pad0, pad1;
+  int n_ep_logged, q_init_on, aborted, pad1;
   unsigned long long active_mask, malf_prev_mask, at_dest_mask, done_mask;
   unsigned long long decisions, ticks, train_ticks;
   double cum_reward;
@@ -442,7 +442,12 @@ SFL_FN void decide(Env e, const sfl_hparams *hp, int env_id, int t) {
   for (int k = 0; k < P; k++)
     if (!port_blocked(e, c_m.port[p0 + k].x, p0 + k, t, now)) semb |= 1 << k;
   int cur = my_port - p0;
-  if (cur < 0 || cur >= P) { h->err |= SFL_ERR_NO_TRAIN_AT_SWITCH; cur = 0; }
+  if (cur < 0 || cur >= P) {
+    // observer.py:294-307: "No train detected at active switch" -- the reference then dies on an unbound current_port
+    // (:307).  There is nothing to be faithful to past this point: flag the env, abandon the episode, carry on.
+    h->err |= SFL_ERR_NO_TRAIN_AT_SWITCH; h->aborted++; h->truncated = 1;
+    return;
+  }
   int delay = delay_at(e, tr0.w, pos, dir, now, tr1.y);
   int level = delay <= 0 ? 0 : (delay <= (tr1.y - tr1.x) * 20 ? 1 : 2);           // observer.py:239-244
   unsigned key = (((unsigned)(p0 + cur) * c_L.NT + tr0.w) * 16u + semb) * 3u + level;
@@ -928,6 +933,7 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
     c->decisions = h->decisions; c->ticks = h->ticks; c->train_ticks = h->train_ticks; c->episodes = h->episode;
     c->err = h->err; c->q_rows = h->q_rows; c->halted = h->halted; c->n_dec_logged = h->n_dec_logged;
     c->n_tick_logged = h->n_tick_logged; c->n_ep_logged = h->n_ep_logged; c->elapsed = h->elapsed;
+    c->aborted = h->aborted; c->reserved = 0;
   }
 #if SFL_DEV
   g.sync();
