@@ -432,7 +432,7 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   k<<<grid, threads, smem, (cudaStream_t)stream>>>();
   CU(cudaGetLastError());
 #else
-  static char host_scratch[16 * SFL_MAX_T + 64 + 4 * SFL_MAX_T + 64];
+  static char host_scratch[32 * SFL_MAX_T + 2 * SFL_MAX_T + 16 + 4 * SFL_MAX_T + 64];
   set_constants(c, &ra, stream);
   for (int i = 0; i < c->cfg.n_envs; i++) {
     if (trace) env_run<1, true, true>(i, 0u, host_scratch); else env_run<1, false, true>(i, 0u, host_scratch);

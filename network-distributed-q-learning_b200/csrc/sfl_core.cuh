@@ -60,6 +60,12 @@ template <int G> struct Grp {
   SFL_FN void sync() const { if (G > 1) __syncwarp(mask); }
   SFL_FN unsigned or32(unsigned v) const { return G > 1 ? __reduce_or_sync(mask, v) : v; }
   SFL_FN int any(int p) const { return G > 1 ? __any_sync(mask, p) : p; }
+  // bit i = predicate of the group's lane i
+  SFL_FN unsigned ballot(int p) const {
+    if (G == 1) return p ? 1u : 0u;
+    unsigned b = __ballot_sync(mask, p);
+    return G == 32 ? b : (b >> ((threadIdx.x & 31) & ~(G - 1))) & ((1u << (G & 31)) - 1u);
+  }
 };
 SFL_FN int popc64(unsigned long long v) { return __popcll(v); }
 SFL_FN int ffs64(unsigned long long v) { return __ffsll((long long)v) - 1; }
@@ -74,6 +80,7 @@ template <int G> struct Grp {
   void sync() const {}
   unsigned or32(unsigned v) const { return v; }
   int any(int p) const { return p; }
+  unsigned ballot(int p) const { return p ? 1u : 0u; }
 };
 SFL_FN int popc64(unsigned long long v) { return __builtin_popcountll(v); }
 SFL_FN int ffs64(unsigned long long v) { return __builtin_ffsll((long long)v) - 1; }
@@ -181,15 +188,16 @@ struct Scratch {
   int8_t *occ;             // [T] train standing on my destination cell, or -1
   uint8_t *blk;            // [T] movement blocked
   int *inj;                // [T] replay only: injected malfunction durations of this tick
+  int4 *rng;               // [T] the four malfunction words of the current 4-tick block (one Philox call per train and block)
 };
 #if SFL_DEV
 __host__
 #endif
-SFL_FN unsigned scratch_bytes(int T) { return (unsigned)(16 * T + ((2 * T + 15) / 16) * 16 + ((4 * T + 15) / 16) * 16); }
+SFL_FN unsigned scratch_bytes(int T) { return (unsigned)(32 * T + ((2 * T + 15) / 16) * 16 + ((4 * T + 15) / 16) * 16); }
 SFL_FN Scratch make_scratch(char *p, int T) {
   Scratch s;
-  s.tmp = (int4 *)p; s.occ = (int8_t *)(p + 16 * T); s.blk = (uint8_t *)(p + 17 * T);
-  s.inj = (int *)(p + 16 * T + ((2 * T + 15) / 16) * 16);
+  s.tmp = (int4 *)p; s.rng = (int4 *)(p + 16 * T); s.occ = (int8_t *)(p + 32 * T); s.blk = (uint8_t *)(p + 33 * T);
+  s.inj = (int *)(p + 32 * T + ((2 * T + 15) / 16) * 16);
   return s;
 }
 
@@ -606,12 +614,30 @@ SFL_FN void env_reset(Env e, const Grp<G> &g) {
 }
 
 // ------------------------------------------------------------------------------------------------ one tick (E5-E7, F2-F5)
+// Group-uniform registers carried across the ticks of a launch (every lane of the group holds the same values);
+// the header copy in shared memory is what the decision phase (first lane) reads and writes.
+struct TickRegs {
+  int elapsed, ended, rng_blk;                 // rng_blk: 4-tick block the cached malfunction words belong to (-1: none)
+  unsigned long long active, done, malf_prev;
+  unsigned long long ticks, train_ticks;       // launch-local, added to the header at the end
+};
+
+// Malfunction draw of train t at tick `now` (row F5): one Philox4x32-10 call per (train, 4-tick block), one 32-bit word
+// per tick.  Event iff word < threshold (probability 1 - exp(-rate)); given an event the word is uniform below the
+// threshold, which gives the duration min + U{0..max-min} + 1 without a second word.
+SFL_FN int malf_duration(const sfl_hparams *hp, unsigned w) {
+  if (w >= hp->malf_threshold) return 0;
+  unsigned range = (unsigned)(hp->malf_max - hp->malf_min + 1);
+  return hp->malf_min + (int)(((unsigned long long)w * range) / hp->malf_threshold) + 1;
+}
+
 template <int G, bool TRACE, class Env>
-SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const Grp<G> &g) {
+SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const Grp<G> &g, TickRegs &R) {
   EnvHdr *h = e.h();
   const int T = c_L.T;
-  const int now = h->elapsed + 1;                                        // flatland: _elapsed_steps += 1 first
+  const int now = R.elapsed + 1;                                         // flatland: _elapsed_steps += 1 first
   const int replay_ev = c_ra.replay_ev != 0;
+  const unsigned thr = hp->malf_threshold;
   if (replay_ev) {
     SFL_NU
     for (int t = g.gl; t < T; t += G) sc.inj[t] = 0;
@@ -625,6 +651,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
     }
     g.sync();
   }
+  const int fresh_rng = !replay_ev && thr && (now >> 2) != R.rng_blk;    // group-uniform
   // ---- phase A: per train: plan pop (switch_env.py:304-339) + flatland step part 1 (Appendix B step 2)
   SFL_NU
   for (int t = g.gl; t < T; t += G) {
@@ -633,180 +660,183 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
     int saved = (ta.y >> 16) & 0xFF, prev_act = (ta.y >> 24) & 0xFF;
     unsigned plan = (unsigned)ta.z & 0xFFFFu;
     int pl = ta.z >> 16, mc = ta.w & 0xFFFF;
-    const int4 tr0 = c_m.train0[t];
-    const int pp = p >= 0 ? p : tr0.x, dd = p >= 0 ? d : tr0.y;
-    const unsigned me = mv_entry(pp, dd);
-    int a = A_NOTHING, flags = 0, ecell = -1;
-    if (st != ST_DONE) {
+    // F5 malfunction draw: every train, every tick; applied only when the counter is 0
+    int dur = 0;
+    if (replay_ev) dur = sc.inj[t];
+    else if (thr) {
+      if (fresh_rng) {
+        U4 u = philox4x32((unsigned)(now >> 2), (unsigned)t, 0xA11Fu, 0u, (unsigned)hp->seed, (unsigned)(hp->seed >> 32));
+        sc.rng[t] = make_int4((int)u.x, (int)u.y, (int)u.z, (int)u.w);
+      }
+      dur = malf_duration(hp, ((const unsigned *)&sc.rng[t])[now & 3]);
+    }
+    if (mc == 0 && dur > 0) mc = dur;
+    int src, dst, ecell = -1, nd = d, act = A_NOTHING, a = A_NOTHING, flags = 0;
+    if (st == ST_DONE) { src = dst = -1 - t; }
+    else {
+      int pp = p, dd = d;
+      if (p < 0) { const int4 tr0 = c_m.train0[t]; pp = tr0.x; dd = tr0.y; }
+      const unsigned me = mv_entry(pp, dd);
       if (pl == 0) a = A_FWD;
       else { a = plan & 0xF; prev_act = a; plan >>= 4; pl--; }
       if (p >= 0) { Mv c = mv_apply(me, a, p); ecell = c.valid ? c.cell : p; flags = 1 | (c.valid ? 2 : 0); }
+      // action preprocessing (a is never DO_NOTHING here: the reference always sends an action)
+      act = a;
+      if (st == ST_WAITING) act = A_NOTHING;
+      if ((act == A_LEFT || act == A_RIGHT) && !mv_valid(me, act)) act = A_FWD;
+      if (is_moving(act) && !mv_valid(me, act)) act = A_STOP;
+      if (is_moving(act) && !saved) saved = act;
+      const int upd = (mc == 0) && act != A_STOP;
+      int ncell = p;
+      if (p < 0) { if (saved) { ncell = pp; nd = dd; } }
+      else if (saved && upd) { Mv c = mv_apply(me, saved, p); if (c.valid) { ncell = c.cell; nd = c.dir; } act = saved; }
+      src = p >= 0 ? p : -1 - t;
+      dst = ncell >= 0 ? ncell : src;
     }
-    // F5 malfunction draw: every train, every tick; applied only when the counter is 0
-    int dur;
-    if (replay_ev) dur = sc.inj[t];
-    else {
-      dur = 0;
-      if (hp->malf_threshold) {
-        U4 u = philox4x32((unsigned)now, (unsigned)t, 0xA11Fu, 0u, (unsigned)hp->seed, (unsigned)(hp->seed >> 32));
-        if (u.x < hp->malf_threshold) dur = hp->malf_min + (int)(((unsigned long long)u.y * (unsigned)(hp->malf_max - hp->malf_min + 1)) >> 32) + 1;
-      }
-    }
-    if (mc == 0 && dur > 0) mc = dur;
-    // action preprocessing
-    int act = a;
-    if (act == A_NOTHING) act = (st == ST_MOVING) ? A_FWD : (saved ? saved : A_STOP);
-    if (st == ST_WAITING) act = A_NOTHING;
-    if ((act == A_LEFT || act == A_RIGHT) && !mv_valid(me, act)) act = A_FWD;
-    if (is_moving(act) && !mv_valid(me, act)) act = A_STOP;
-    if (is_moving(act) && !saved && st != ST_DONE) saved = act;
-    int upd = (mc == 0) && act != A_STOP;
-    int ncell = p, nd = d;
-    if (st == ST_DONE) { }
-    else if (p < 0 && saved) { ncell = tr0.x; nd = tr0.y; }
-    else if (saved && upd) { Mv c = mv_apply(me, saved, p); if (c.valid) { ncell = c.cell; nd = c.dir; } act = saved; }
-    int src = p >= 0 ? p : -1 - t;
     ta.y = d | (st << 8) | (saved << 16) | (prev_act << 24);
     ta.z = (int)plan | (pl << 16);
     ta.w = (ta.w & (int)0xFFFF0000) | mc;
     e.tra()[t] = ta;
-    sc.tmp[t] = make_int4(src, ncell >= 0 ? ncell : src, ecell, nd | (act << 8) | (a << 16) | (flags << 24));
+    sc.tmp[t] = make_int4(src, dst, ecell, nd | (act << 8) | (a << 16) | (flags << 24));
   }
+  if (fresh_rng) R.rng_blk = now >> 2;
   g.sync();
   // ---- phase B: motion check (F3)
+  unsigned long long chain = 0;               // trains whose destination is occupied by a train that is itself moving
   SFL_NU
-  for (int t = g.gl; t < T; t += G) {
-    int4 m = sc.tmp[t];
-    int s = m.x, d = m.y;
-    int wants = d != s, blocked = !wants, occ = -1;
-    if (wants) {
-      SFL_NU
-      for (int k = 0; k < T; k++) {
-        if (k == t) continue;
-        int4 o = sc.tmp[k];
-        if (o.x == d) occ = k;
-        if (o.y == d && o.y != o.x && k < t) blocked = 1;              // lowest handle wins a contended cell
+  for (int base = 0; base < T; base += G) {
+    const int t = base + g.gl;
+    int follows = 0;
+    if (t < T) {
+      int4 m = sc.tmp[t];
+      int s = m.x, d = m.y;
+      int wants = d != s, blocked = !wants, occ = -1;
+      if (wants) {
+        SFL_NU
+        for (int k = 0; k < T; k++) {
+          int2 o = *(const int2 *)&sc.tmp[k];
+          if (o.x == d) occ = k;                                         // k != t: my own src differs from my dst
+          if (o.y == d && o.y != o.x && k < t) blocked = 1;              // lowest handle wins a contended cell
+        }
+        if (occ >= 0) { int2 o = *(const int2 *)&sc.tmp[occ]; if (o.y == s && o.y != o.x) blocked = 1; }   // swap
       }
-      if (occ >= 0) { int4 o = sc.tmp[occ]; if (o.y == s && o.y != o.x) blocked = 1; }   // swap
+      sc.occ[t] = (int8_t)occ; sc.blk[t] = (uint8_t)blocked;
+      follows = !blocked && occ >= 0;
     }
-    sc.occ[t] = (int8_t)occ; sc.blk[t] = (uint8_t)blocked;
+    chain |= (unsigned long long)g.ballot(follows) << base;
   }
   g.sync();
-  SFL_NU
-  for (int iter = 0; iter < T; iter++) {                                // chains: fixed point (monotone)
-    int changed = 0;
+  if (chain) {                                                            // chains: fixed point (monotone), group-uniform
     SFL_NU
-    for (int t = g.gl; t < T; t += G) {
-      int occ = sc.occ[t];
-      if (!sc.blk[t] && occ >= 0 && ((volatile uint8_t *)sc.blk)[occ]) { sc.blk[t] = 1; changed = 1; }
+    for (int iter = 0; iter < T; iter++) {
+      int changed = 0;
+      SFL_NU
+      for (int t = g.gl; t < T; t += G) {
+        int occ = sc.occ[t];
+        if (!sc.blk[t] && occ >= 0 && ((volatile uint8_t *)sc.blk)[occ]) { sc.blk[t] = 1; changed = 1; }
+      }
+      g.sync();
+      if (!g.any(changed)) break;
     }
-    g.sync();
-    if (!g.any(changed)) break;
   }
   // ---- phase C: state machine + position update (Appendix B steps 4-5), held-back trains (switch_env.py:353-367),
   //      and _check_active_switch (switch_env.py:427-485), which reads only the train's own new state
-  unsigned done_lo = 0, done_hi = 0, malf_lo = 0, malf_hi = 0, stop_lo = 0, stop_hi = 0, dep_lo = 0, dep_hi = 0, act_lo = 0, act_hi = 0;
+  unsigned long long done_bits = 0, malf_bits = 0, stopped_bits = 0, depart_bits = 0, active = 0;
   SFL_NU
-  for (int t = g.gl; t < T; t += G) {
-    int4 ta = e.tra()[t];
-    const int4 m = sc.tmp[t];
-    int p = ta.x, d = ta.y & 0xFF;
-    const int st = (ta.y >> 8) & 0xFF;
-    int saved = (ta.y >> 16) & 0xFF;
-    const int prev_act = (ta.y >> 24) & 0xFF;
-    unsigned plan = (unsigned)ta.z & 0xFFFFu;
-    int pl = ta.z >> 16, mc = ta.w & 0xFFFF, next_port = (int)((unsigned)ta.w >> 16);
-    const int act = (m.w >> 8) & 0xFF, popped = (m.w >> 16) & 0xFF, fl = (m.w >> 24) & 0xFF;
-    const int wants = m.y != m.x;
-    const int in_malf = mc > 0, allowed = !in_malf && wants && !sc.blk[t];
-    const int4 tr0 = c_m.train0[t], tr1 = c_m.train1[t];
-    const int ed_reached = now >= tr1.x, stop_given = act == A_STOP, valid_move = is_moving(act) && allowed, conflict = !allowed;
-    int nxt = st;
-    switch (st) {
-      case ST_WAITING: if (in_malf) nxt = ST_MALF_OFF; else if (ed_reached) nxt = ST_READY; break;
-      case ST_READY: if (in_malf) nxt = ST_MALF_OFF; else if (valid_move) nxt = ST_MOVING; break;
-      case ST_MALF_OFF:
-        if (!in_malf) { if (ed_reached) nxt = valid_move ? ST_MOVING : (stop_given ? ST_STOPPED : ST_READY); else nxt = ST_WAITING; }
-        break;
-      case ST_MOVING: if (in_malf) nxt = ST_MALF; else if (stop_given || conflict) nxt = ST_STOPPED; break;
-      case ST_STOPPED: if (in_malf) nxt = ST_MALF; else if (valid_move) nxt = ST_MOVING; break;
-      case ST_MALF: if (!in_malf && valid_move) nxt = ST_MOVING; else if (!in_malf && (stop_given || conflict)) nxt = ST_STOPPED; break;
-      default: break;
-    }
-    if (nxt >= ST_MOVING && nxt <= ST_MALF) {
-      if (st <= ST_MALF_OFF) { p = tr0.x; d = tr0.y; }
-      else if (allowed) { p = m.y; d = m.w & 0xFF; if (p == tr0.z) nxt = ST_DONE; }
-    }
-    if (nxt == ST_DONE) p = -1;
-    if (mc > 0) mc--;
-    if (p >= 0) saved = 0;
-    const unsigned bit_lo = t < 32 ? 1u << t : 0u, bit_hi = t >= 32 ? 1u << (t - 32) : 0u;
-    if (nxt == ST_DONE) { done_lo |= bit_lo; done_hi |= bit_hi; }
-    if (mc != 0) { malf_lo |= bit_lo; malf_hi |= bit_hi; }
-    if (nxt == ST_STOPPED || nxt == ST_MALF) { stop_lo |= bit_lo; stop_hi |= bit_hi; }
-    if (now == tr1.x - 2) { dep_lo |= bit_lo; dep_hi |= bit_hi; }
-    if (TRACE) {
-      if (c_ra.trace_tick && h->n_tick_logged < c_ra.tick_cap) {
-        sfl_tick_rec *rec = c_ra.trace_tick + ((size_t)env_id * c_ra.tick_cap + h->n_tick_logged) * T + t;
-        rec->pos = p; rec->dir = (int8_t)d; rec->state = (int8_t)nxt; rec->malf = (int16_t)mc;
+  for (int base = 0; base < T; base += G) {
+    const int t = base + g.gl;
+    int f_done = 0, f_malf = 0, f_stop = 0, f_dep = 0, f_act = 0;
+    if (t < T) {
+      int4 ta = e.tra()[t];
+      const int4 m = sc.tmp[t];
+      int p = ta.x, d = ta.y & 0xFF;
+      const int st = (ta.y >> 8) & 0xFF;
+      int saved = (ta.y >> 16) & 0xFF;
+      const int prev_act = (ta.y >> 24) & 0xFF;
+      unsigned plan = (unsigned)ta.z & 0xFFFFu;
+      int pl = ta.z >> 16, mc = ta.w & 0xFFFF, next_port = (int)((unsigned)ta.w >> 16);
+      const int act = (m.w >> 8) & 0xFF, popped = (m.w >> 16) & 0xFF, fl = (m.w >> 24) & 0xFF;
+      const int wants = m.y != m.x;
+      const int in_malf = mc > 0, allowed = !in_malf && wants && !sc.blk[t];
+      const int4 tr0 = c_m.train0[t];
+      const int ed = c_m.train1[t].x;
+      const int ed_reached = now >= ed, stop_given = act == A_STOP, valid_move = is_moving(act) && allowed, conflict = !allowed;
+      int nxt = st;
+      switch (st) {
+        case ST_WAITING: if (in_malf) nxt = ST_MALF_OFF; else if (ed_reached) nxt = ST_READY; break;
+        case ST_READY: if (in_malf) nxt = ST_MALF_OFF; else if (valid_move) nxt = ST_MOVING; break;
+        case ST_MALF_OFF:
+          if (!in_malf) { if (ed_reached) nxt = valid_move ? ST_MOVING : (stop_given ? ST_STOPPED : ST_READY); else nxt = ST_WAITING; }
+          break;
+        case ST_MOVING: if (in_malf) nxt = ST_MALF; else if (stop_given || conflict) nxt = ST_STOPPED; break;
+        case ST_STOPPED: if (in_malf) nxt = ST_MALF; else if (valid_move) nxt = ST_MOVING; break;
+        case ST_MALF: if (!in_malf && valid_move) nxt = ST_MOVING; else if (!in_malf && (stop_given || conflict)) nxt = ST_STOPPED; break;
+        default: break;
       }
-    }
-    // flatland held the train back (switch_env.py:353-367)
-    if ((fl & 1) && (fl & 2) && m.z != p && popped != A_STOP) {
-      if (pl >= SFL_PLAN_CAP) { h->err |= SFL_ERR_PLAN_FULL; pl = SFL_PLAN_CAP - 1; }
-      plan = ((plan << 4) | (unsigned)popped) & 0xFFFFu; pl++;
-      if (c_m.cell_switch[m.z] >= 0) {
-        int src_port = (int)((unsigned)e.trb()[t].x >> 16);
-        if (src_port != 0xFFFF) next_port = src_port;
+      if (nxt >= ST_MOVING && nxt <= ST_MALF) {
+        if (st <= ST_MALF_OFF) { p = tr0.x; d = tr0.y; }
+        else if (allowed) { p = m.y; d = m.w & 0xFF; if (p == tr0.z) nxt = ST_DONE; }
       }
-    }
-    // _check_active_switch (switch_env.py:427-485)
-    if (p >= 0 && nxt != ST_WAITING) {
-      int peek = pl ? (int)(plan & 0xF) : A_FWD;
-      Mv c = check_action(peek, p, d);
-      int s = c_m.cell_switch[c.cell];
-      if (s >= 0) {
-        int ok = 1;
-        if (nxt == ST_MOVING || nxt == ST_READY) { }
-        else if ((nxt == ST_STOPPED || nxt == ST_MALF) && prev_act == A_STOP) { }
-        else if (nxt == ST_STOPPED || nxt == ST_MALF) s = c_m.port[next_port].w;
-        else ok = 0;
-        if (ok) {
-          ((uint16_t *)&e.trb()[t].y)[0] = (uint16_t)s;
-          act_lo |= bit_lo; act_hi |= bit_hi;
+      if (nxt == ST_DONE) p = -1;
+      if (mc > 0) mc--;
+      if (p >= 0) saved = 0;
+      f_done = nxt == ST_DONE; f_malf = mc != 0; f_stop = nxt == ST_STOPPED || nxt == ST_MALF; f_dep = now == ed - 2;
+      if (TRACE) {
+        if (c_ra.trace_tick && h->n_tick_logged < c_ra.tick_cap) {
+          sfl_tick_rec *rec = c_ra.trace_tick + ((size_t)env_id * c_ra.tick_cap + h->n_tick_logged) * T + t;
+          rec->pos = p; rec->dir = (int8_t)d; rec->state = (int8_t)nxt; rec->malf = (int16_t)mc;
         }
       }
+      // flatland held the train back (switch_env.py:353-367)
+      if ((fl & 1) && (fl & 2) && m.z != p && popped != A_STOP) {
+        if (pl >= SFL_PLAN_CAP) { h->err |= SFL_ERR_PLAN_FULL; pl = SFL_PLAN_CAP - 1; }
+        plan = ((plan << 4) | (unsigned)popped) & 0xFFFFu; pl++;
+        if (c_m.cell_switch[m.z] >= 0) {
+          int src_port = (int)((unsigned)e.trb()[t].x >> 16);
+          if (src_port != 0xFFFF) next_port = src_port;
+        }
+      }
+      // _check_active_switch (switch_env.py:427-485)
+      if (p >= 0 && nxt != ST_WAITING) {
+        int peek = pl ? (int)(plan & 0xF) : A_FWD;
+        Mv c = check_action(peek, p, d);
+        int s = c_m.cell_switch[c.cell];
+        if (s >= 0) {
+          int ok = 1;
+          if (nxt == ST_MOVING || nxt == ST_READY) { }
+          else if ((nxt == ST_STOPPED || nxt == ST_MALF) && prev_act == A_STOP) { }
+          else if (nxt == ST_STOPPED || nxt == ST_MALF) s = c_m.port[next_port].w;
+          else ok = 0;
+          if (ok) { ((uint16_t *)&e.trb()[t].y)[0] = (uint16_t)s; f_act = 1; }
+        }
+      }
+      ta.x = p;
+      ta.y = d | (nxt << 8) | (saved << 16) | (prev_act << 24);
+      ta.z = (int)plan | (pl << 16);
+      ta.w = mc | (next_port << 16);
+      e.tra()[t] = ta;
     }
-    ta.x = p;
-    ta.y = d | (nxt << 8) | (saved << 16) | (prev_act << 24);
-    ta.z = (int)plan | (pl << 16);
-    ta.w = mc | (next_port << 16);
-    e.tra()[t] = ta;
-  }
-  unsigned long long done_bits, malf_bits, stopped_bits, depart_bits, active;
-  {
-    done_lo = g.or32(done_lo); malf_lo = g.or32(malf_lo); stop_lo = g.or32(stop_lo); dep_lo = g.or32(dep_lo); act_lo = g.or32(act_lo);
-    if (T > 32) { done_hi = g.or32(done_hi); malf_hi = g.or32(malf_hi); stop_hi = g.or32(stop_hi); dep_hi = g.or32(dep_hi); act_hi = g.or32(act_hi); }
-    done_bits = ((unsigned long long)done_hi << 32) | done_lo; malf_bits = ((unsigned long long)malf_hi << 32) | malf_lo;
-    stopped_bits = ((unsigned long long)stop_hi << 32) | stop_lo; depart_bits = ((unsigned long long)dep_hi << 32) | dep_lo;
-    active = ((unsigned long long)act_hi << 32) | act_lo;
+    done_bits |= (unsigned long long)g.ballot(f_done) << base;
+    malf_bits |= (unsigned long long)g.ballot(f_malf) << base;
+    stopped_bits |= (unsigned long long)g.ballot(f_stop) << base;
+    depart_bits |= (unsigned long long)g.ballot(f_dep) << base;
+    active |= (unsigned long long)g.ballot(f_act) << base;
   }
   const unsigned long long all_mask = T >= 64 ? ~0ull : ((1ull << T) - 1ull);
-  const int all_done = done_bits == all_mask;
-  const int ended = all_done || now >= c_m.max_episode_steps;             // dones["__all__"] (Appendix B step 6)
-  const unsigned long long prev_done = h->done_mask;
-  g.sync();
+  const int ended = done_bits == all_mask || now >= c_m.max_episode_steps;   // dones["__all__"] (Appendix B step 6)
+  const unsigned long long prev_done = R.done;
   // ---- phase D2: semaphores of done trains (switch_env.py:370-376); every train counts as done at the end
   if ((done_bits & ~prev_done) || ended) {
+    g.sync();
     SFL_NU
     for (int p = g.gl; p < c_L.NP; p += G) {
       int tr = e.sem()[p].z;
       if (tr >= 0 && (ended || ((done_bits >> tr) & 1))) e.sem()[p].z = -1;
     }
-    g.sync();
   }
   // ---- phase D3: departure bookings (switch_env.py:379-384), train order
   if (depart_bits) {
+    g.sync();
     if (g.gl == 0) {
       unsigned long long b = depart_bits;
       SFL_NU
@@ -816,10 +846,10 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
         e.sem()[(unsigned)e.tra()[t].w >> 16] = make_int4(tr1.x - 2, tr1.x + tr1.w, t, SEM_IN);
       }
     }
-    g.sync();
   }
   // ---- phase D4: extend_semaphores (rail_network.py:229-244)
   if (stopped_bits) {
+    g.sync();
     SFL_NU
     for (int p = g.gl; p < c_L.NP; p += G) {
       int4 r = e.sem()[p];
@@ -841,15 +871,15 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
   }
   if (g.gl == 0) {
     h->elapsed = now;
-    h->done_mask = done_bits;
-    h->terminated = ended;
-    h->num_malf += popc64(malf_bits & ~h->malf_prev_mask);             // switch_env.py:399-401
-    h->malf_prev_mask = malf_bits;
-    h->active_mask = active;
-    h->ticks++;
-    h->train_ticks += (unsigned long long)(T - popc64(prev_done));
+    const unsigned long long new_malf = malf_bits & ~R.malf_prev;
+    if (new_malf) h->num_malf += popc64(new_malf);                       // switch_env.py:399-401
+    if (done_bits != prev_done) h->done_mask = done_bits;
+    if (ended) h->terminated = 1;
+    if (active) h->active_mask = active;                                 // the queue is empty whenever a tick runs
     if (TRACE) { if (c_ra.trace_tick) h->n_tick_logged++; }
   }
+  R.elapsed = now; R.ended = ended; R.active = active; R.done = done_bits; R.malf_prev = malf_bits;
+  R.ticks++; R.train_ticks += (unsigned long long)(T - popc64(prev_done));
   g.sync();
 }
 
@@ -906,29 +936,43 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
   sc = make_scratch(host_scratch, c_L.T);
 #endif
   EnvHdr *h = e.h();
+  TickRegs R;
+  R.elapsed = h->elapsed; R.ended = h->terminated | h->truncated; R.rng_blk = -1;
+  R.active = h->active_mask; R.done = h->done_mask; R.malf_prev = h->malf_prev_mask;
+  R.ticks = 0; R.train_ticks = 0;
+  int need_reset = h->need_reset, halted = h->halted;
   SFL_NU
   for (int it = 0; it < c_ra.max_ticks; it++) {
-    if (h->halted) continue;
-    if (g.gl == 0) {
-      SFL_NU
-      for (;;) {                                                          // agent_iter: FIFO in train-handle order
-        if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<TRACE>(e, hp, env_id);
-        if (h->terminated || h->truncated || !h->active_mask) break;
-        int t = ffs64(h->active_mask);
-        h->active_mask &= h->active_mask - 1;
-        decide<TRACE>(e, hp, env_id, t);
+    if (halted) break;
+    if (R.active || R.ended) {                                            // group-uniform: something is due before the tick
+      if (g.gl == 0) {
+        SFL_NU
+        for (;;) {                                                        // agent_iter: FIFO in train-handle order
+          if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<TRACE>(e, hp, env_id);
+          if (h->terminated || h->truncated || !h->active_mask) break;
+          int t = ffs64(h->active_mask);
+          h->active_mask &= h->active_mask - 1;
+          decide<TRACE>(e, hp, env_id, t);
+        }
+        if (h->terminated || h->truncated) episode_end(e, env_id);
       }
-      if (h->terminated || h->truncated) episode_end(e, env_id);
+      g.sync();
+      need_reset = h->need_reset;
+      R.active = 0;
     }
-    g.sync();
-    if (h->need_reset) {
-      if (hp->episodes >= 0 && h->episode >= hp->episodes) { g.sync(); if (g.gl == 0) h->halted = 1; g.sync(); continue; }
+    if (need_reset) {
+      if (hp->episodes >= 0 && h->episode >= hp->episodes) { halted = 1; break; }
       env_reset<G>(e, g);
+      need_reset = 0;
+      R.elapsed = 0; R.ended = 0; R.rng_blk = -1; R.active = 0; R.done = 0; R.malf_prev = 0;
     }
-    env_tick<G, TRACE>(e, sc, hp, env_id, g);
+    env_tick<G, TRACE>(e, sc, hp, env_id, g, R);
   }
   g.sync();
   if (g.gl == 0) {
+    h->halted = halted;
+    h->malf_prev_mask = R.malf_prev;
+    h->ticks += R.ticks; h->train_ticks += R.train_ticks;
     sfl_env_counters *c = c_ra.counters + env_id;
     c->decisions = h->decisions; c->ticks = h->ticks; c->train_ticks = h->train_ticks; c->episodes = h->episode;
     c->err = h->err; c->q_rows = h->q_rows; c->halted = h->halted; c->n_dec_logged = h->n_dec_logged;
