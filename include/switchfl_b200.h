@@ -144,9 +144,9 @@ int sfl_bind(void *ctx, const sfl_buffers *bufs);
  * on the device.  keep_q != 0 keeps Q tables and interaction counters (a new learn()/test() call).     */
 int sfl_reset(void *ctx, int keep_q, void *stream);
 
-/* Lanes of a warp that cooperate on one environment (1, 2, 4, 8, 16 or 32; 32/lanes environments share a warp).
- * sfl_create picks the smallest count that still gives every SM scheduler >= 8 warps for cfg.n_envs; this overrides
- * it.  A scheduling choice only: results do not depend on it.                                          */
+/* Lanes of a warp that cooperate on one environment (1, 2, 4, 8, 16 or 32; 32/lanes environments share a warp and
+ * one instruction stream).  sfl_create picks max(lanes that cover the trains in one pass, lanes that still give the
+ * batch ~3.5 warps per SM scheduler); this overrides it.  A scheduling choice only: results do not depend on it.  */
 int sfl_set_lanes(void *ctx, int lanes);
 int sfl_get_lanes(void *ctx);
 

@@ -94,10 +94,9 @@ __global__ void __launch_bounds__(SFL_CTA_THREADS) k_init(InitArgs ia) {
 // lists and -- when they fit -- semaphores, rewards and per-switch counters) is staged once per launch and written
 // back at the end, so the tick / decision loops touch HBM only for Q rows.
 template <int G, bool TRACE, bool TH>
-__global__ void __launch_bounds__(SFL_CTA_THREADS, G == 32 ? 7 : 4) k_run() {
+__global__ void __launch_bounds__(SFL_CTA_THREADS, (G == 32 || !TH) ? 7 : 4) k_run() {
   const int slot = threadIdx.x / G;                    // environment slot inside the CTA
   const int env_id = blockIdx.x * (blockDim.x / G) + slot;
-  if (env_id >= c_ra.n_envs) return;                   // whole groups leave together
   env_run<G, TRACE, TH>(env_id, (unsigned)slot * c_ra.env_smem, nullptr);
 }
 
@@ -146,7 +145,7 @@ static int choose_hot(Ctx *c) {
   const unsigned fixed = (unsigned)sizeof(sfl_hparams) + scratch_bytes(c->L.T);
   const unsigned per_warp = 32u / (unsigned)c->lanes;
   if ((size_t)(c->L.off_q + fixed) * per_warp <= 14u * 1024u) { c->tail_hot = 1; c->hot_bytes = c->L.off_q; }   // >= 16 warps per SM
-  else { c->tail_hot = 0; c->hot_bytes = c->L.off_sem; }
+  else { c->tail_hot = 0; c->hot_bytes = c->L.off_pend; }
   c->env_smem = c->hot_bytes + fixed;
   return (size_t)c->env_smem * per_warp > 227u * 1024u;
 }
@@ -321,17 +320,19 @@ int sfl_create(const sfl_map_desc *map, const sfl_config *cfg, int device, void 
   m.dist.p = (const int *)(b + o_dist); m.qinit.p = (const int8_t *)(b + o_qi);
   c->lanes = 32;
   choose_hot(c);
-  // lanes per environment: as few as keep every scheduler of the GPU busy (>= 8 warps each), at least 1
+  // Lanes per environment, from measurements on B200: wide enough that one pass covers the
+  // trains (lane = train), and wide enough that the batch still fills ~3.5 warps per SM scheduler -- below that the
+  // serial per-environment chains cannot hide their own latency; narrower groups share one instruction stream
+  // between the 32/G environments of a warp.
   {
-    long warps_wanted = (long)sm_count * 4 * 8;
-    int G = 32;
-    while (G > 1 && (long)cfg->n_envs * (G / 2) / 32 >= warps_wanted) {
-      c->lanes = G / 2;
-      if (choose_hot(c)) break;
-      G /= 2;
-    }
+    int g_trains = 1;
+    while (g_trains < T && g_trains < 32) g_trains *= 2;
+    const long warps_wanted = (long)sm_count * 14;
+    int g_warps = 1;
+    while (g_warps < 32 && (long)cfg->n_envs * g_warps / 32 < warps_wanted) g_warps *= 2;
+    int G = g_trains > g_warps ? g_trains : g_warps;
     c->lanes = G;
-    choose_hot(c);
+    while (choose_hot(c) && G < 32) { G *= 2; c->lanes = G; }
   }
   *ctx_out = c;
   return SFL_OK;
@@ -432,7 +433,7 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   k<<<grid, threads, smem, (cudaStream_t)stream>>>();
   CU(cudaGetLastError());
 #else
-  static char host_scratch[32 * SFL_MAX_T + 2 * SFL_MAX_T + 16 + 4 * SFL_MAX_T + 64];
+  static char host_scratch[32 * SFL_MAX_T + 2 * SFL_MAX_T + 64];
   set_constants(c, &ra, stream);
   for (int i = 0; i < c->cfg.n_envs; i++) {
     if (trace) env_run<1, true, true>(i, 0u, host_scratch); else env_run<1, false, true>(i, 0u, host_scratch);

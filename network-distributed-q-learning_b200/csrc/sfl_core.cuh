@@ -48,24 +48,28 @@ enum { SEM_IN = 0, SEM_OUT = 1 };
 #define SFL_PLAN_CAP 4
 
 // ------------------------------------------------------------------------------------------------ lane groups
+// A group = G consecutive lanes of a warp working on one environment.  Every collective below is issued by the WHOLE
+// warp (full member mask) at warp-uniform points of the control flow: group-masked __syncwarp / votes let the groups of
+// a warp drift apart, after which the warp executes the sum of their instruction streams instead of one shared stream.
+// Branch conditions that guard a collective are therefore made warp-uniform with wany(); a group for which the
+// condition does not hold walks through with its own predicate false.
 #if SFL_DEV
 template <int G> struct Grp {
-  unsigned mask;             // the lanes of my group inside the warp
   int gl;                    // my lane inside the group
+  int shift;                 // first lane of my group inside the warp
   SFL_FN Grp() {
     int lane = threadIdx.x & 31;
     gl = lane & (G - 1);
-    mask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
+    shift = lane & ~(G - 1);
   }
-  SFL_FN void sync() const { if (G > 1) __syncwarp(mask); }
-  SFL_FN unsigned or32(unsigned v) const { return G > 1 ? __reduce_or_sync(mask, v) : v; }
-  SFL_FN int any(int p) const { return G > 1 ? __any_sync(mask, p) : p; }
+  SFL_FN void sync() const { __syncwarp(); }
+  SFL_FN int wany(int p) const { return __any_sync(0xffffffffu, p); }          // over the warp
   // bit i = predicate of the group's lane i
   SFL_FN unsigned ballot(int p) const {
-    if (G == 1) return p ? 1u : 0u;
-    unsigned b = __ballot_sync(mask, p);
-    return G == 32 ? b : (b >> ((threadIdx.x & 31) & ~(G - 1))) & ((1u << (G & 31)) - 1u);
+    unsigned b = __ballot_sync(0xffffffffu, p);
+    return G == 32 ? b : (b >> shift) & ((1u << (G & 31)) - 1u);
   }
+  SFL_FN int any(int p) const { return ballot(p) != 0u; }                       // over the group
 };
 SFL_FN int popc64(unsigned long long v) { return __popcll(v); }
 SFL_FN int ffs64(unsigned long long v) { return __ffsll((long long)v) - 1; }
@@ -75,12 +79,12 @@ SFL_FN double dadd(double a, double b) { return __dadd_rn(a, b); }
 template <class T> SFL_FN T ldg(const T *p) { return __ldg(p); }
 #else
 template <int G> struct Grp {
-  unsigned mask; int gl;
-  Grp() : mask(1u), gl(0) {}
+  int gl, shift;
+  Grp() : gl(0), shift(0) {}
   void sync() const {}
-  unsigned or32(unsigned v) const { return v; }
-  int any(int p) const { return p; }
+  int wany(int p) const { return p; }
   unsigned ballot(int p) const { return p ? 1u : 0u; }
+  int any(int p) const { return p; }
 };
 SFL_FN int popc64(unsigned long long v) { return __builtin_popcountll(v); }
 SFL_FN int ffs64(unsigned long long v) { return __builtin_ffsll((long long)v) - 1; }
@@ -133,7 +137,7 @@ struct EnvHdr {            // 128 bytes at the start of every env block
 //   TrA {pos, dir | state<<8 | saved<<16 | prev_act<<24, plan (4 bits per entry, head lowest) | plan_len<<16, malf (u16) | next_port<<16}
 //   TrB {prev_port (u16) | source_port<<16 (0xFFFF = none), act_switch (u16) | pend_n<<16, last_delay, 0}
 // Per-switch record SwS {interactions, 0, eps_pow (f64) = epsilon_decay_rate ** interactions}.
-// Pending update (distr_q.py:340-342): {key, next_sw | prev_sw<<12 | action<<24}.
+// Pending update (distr_q.py:340-342): {key, next_sw | prev_sw<<12 | action<<24}; part of the tail (decision phase only).
 // Semaphore record (rail_network.py:133): {t0, t1, train (-1 = absent), type}.
 struct SwS { int ninter, pad; double eps_pow; };
 
@@ -172,8 +176,8 @@ template <bool TH> struct EnvT {
   SFL_FN EnvHdr *h() const { return (EnvHdr *)hot_ptr(hot); }
   SFL_FN int4 *tra() const { return (int4 *)(hot_ptr(hot) + c_L.off_tra); }
   SFL_FN int4 *trb() const { return (int4 *)(hot_ptr(hot) + c_L.off_trb); }
-  SFL_FN int2 *pend() const { return (int2 *)(hot_ptr(hot) + c_L.off_pend); }
   SFL_FN char *tail() const { return TH ? hot_ptr(hot) : gb; }
+  SFL_FN int2 *pend() const { return (int2 *)(tail() + c_L.off_pend); }
   SFL_FN int4 *sem() const { return (int4 *)(tail() + c_L.off_sem); }
   SFL_FN int *rewards() const { return (int *)(tail() + c_L.off_rewards); }
   SFL_FN SwS *sws() const { return (SwS *)(tail() + c_L.off_sws); }
@@ -193,11 +197,11 @@ struct Scratch {
 #if SFL_DEV
 __host__
 #endif
-SFL_FN unsigned scratch_bytes(int T) { return (unsigned)(32 * T + ((2 * T + 15) / 16) * 16 + ((4 * T + 15) / 16) * 16); }
+SFL_FN unsigned scratch_bytes(int T) { return (unsigned)(32 * T + ((2 * T + 15) / 16) * 16); }
 SFL_FN Scratch make_scratch(char *p, int T) {
   Scratch s;
   s.tmp = (int4 *)p; s.rng = (int4 *)(p + 16 * T); s.occ = (int8_t *)(p + 32 * T); s.blk = (uint8_t *)(p + 33 * T);
-  s.inj = (int *)(p + 32 * T + ((2 * T + 15) / 16) * 16);
+  s.inj = (int *)s.rng;                        // replay injects recorded events instead of drawing: the areas never coexist
   return s;
 }
 
@@ -584,11 +588,13 @@ SFL_FN void decide(Env e, const sfl_hparams *hp, int env_id, int t) {
 
 // ------------------------------------------------------------------------------------------------ reset (E1)
 // switch_env.py:93-158 with a constant map: state re-init + the precomputed _init_ports table (:507-568)
+// (`on`: this group resets; the syncs are the whole warp's)
 template <int G, class Env>
-SFL_FN void env_reset(Env e, const Grp<G> &g) {
+SFL_FN void env_reset(Env e, const Grp<G> &g, int on) {
   EnvHdr *h = e.h();
+  const int T = on ? c_L.T : 0, NP = on ? c_L.NP : 0;
   SFL_NU
-  for (int t = g.gl; t < c_L.T; t += G) {
+  for (int t = g.gl; t < T; t += G) {
     int4 tr0 = c_m.train0[t], tr1 = c_m.train1[t];
     e.tra()[t] = make_int4(-1, tr0.y | (ST_WAITING << 8) | (0 << 16) | (A_NONE << 24), 0, (int)((unsigned)tr1.z << 16));
     int4 b = e.trb()[t];
@@ -596,13 +602,13 @@ SFL_FN void env_reset(Env e, const Grp<G> &g) {
     e.trb()[t] = make_int4(b.x, 0xFFFF, c_m.init_delay[t], 0);
   }
   SFL_NU
-  for (int p = g.gl; p < c_L.NP; p += G) e.sem()[p] = make_int4(0, 0, -1, 0);
+  for (int p = g.gl; p < NP; p += G) e.sem()[p] = make_int4(0, 0, -1, 0);
   SFL_NU
-  for (int i = g.gl; i < c_L.S * c_L.T; i += G) e.rewards()[i] = 0;
+  for (int i = g.gl; i < c_L.S * T; i += G) e.rewards()[i] = 0;
   g.sync();
-  if (g.gl == 0) {
+  if (on && g.gl == 0) {
     SFL_NU
-    for (int t = 0; t < c_L.T; t++) {                                     // switch_env.py:564-568, train order
+    for (int t = 0; t < T; t++) {                                         // switch_env.py:564-568, train order
       int4 tr1 = c_m.train1[t];
       e.sem()[tr1.z] = make_int4(tr1.x - 2, tr1.x + tr1.w, t, SEM_IN);
     }
@@ -632,17 +638,20 @@ SFL_FN int malf_duration(const sfl_hparams *hp, unsigned w) {
 }
 
 template <int G, bool TRACE, class Env>
-SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const Grp<G> &g, TickRegs &R) {
+// `live` = this group's environment takes part (not halted, not an idle slot of the last warp); every loop bound and
+// branch that contains a collective is warp-uniform, the per-group work inside is predicated.
+SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const Grp<G> &g, TickRegs &R, const int live) {
   EnvHdr *h = e.h();
-  const int T = c_L.T;
+  const int Tw = c_L.T;                                                  // warp-uniform loop bound
+  const int T = live ? Tw : 0;
   const int now = R.elapsed + 1;                                         // flatland: _elapsed_steps += 1 first
   const int replay_ev = c_ra.replay_ev != 0;
-  const unsigned thr = hp->malf_threshold;
+  const unsigned thr = live ? hp->malf_threshold : 0u;
   if (replay_ev) {
     SFL_NU
     for (int t = g.gl; t < T; t += G) sc.inj[t] = 0;
     g.sync();
-    if (g.gl == 0) {
+    if (live && g.gl == 0) {
       const int *ev = c_ra.replay_ev + (size_t)env_id * c_ra.ev_cap * 3;
       int c = h->ev_cursor;
       SFL_NU
@@ -704,7 +713,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
   // ---- phase B: motion check (F3)
   unsigned long long chain = 0;               // trains whose destination is occupied by a train that is itself moving
   SFL_NU
-  for (int base = 0; base < T; base += G) {
+  for (int base = 0; base < Tw; base += G) {
     const int t = base + g.gl;
     int follows = 0;
     if (t < T) {
@@ -726,24 +735,26 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
     chain |= (unsigned long long)g.ballot(follows) << base;
   }
   g.sync();
-  if (chain) {                                                            // chains: fixed point (monotone), group-uniform
+  if (g.wany(chain != 0)) {                                               // chains: fixed point (monotone)
     SFL_NU
-    for (int iter = 0; iter < T; iter++) {
+    for (int iter = 0; iter < Tw; iter++) {
       int changed = 0;
-      SFL_NU
-      for (int t = g.gl; t < T; t += G) {
-        int occ = sc.occ[t];
-        if (!sc.blk[t] && occ >= 0 && ((volatile uint8_t *)sc.blk)[occ]) { sc.blk[t] = 1; changed = 1; }
+      if (chain) {
+        SFL_NU
+        for (int t = g.gl; t < T; t += G) {
+          int occ = sc.occ[t];
+          if (!sc.blk[t] && occ >= 0 && ((volatile uint8_t *)sc.blk)[occ]) { sc.blk[t] = 1; changed = 1; }
+        }
       }
       g.sync();
-      if (!g.any(changed)) break;
+      if (!g.wany(changed)) break;
     }
   }
   // ---- phase C: state machine + position update (Appendix B steps 4-5), held-back trains (switch_env.py:353-367),
   //      and _check_active_switch (switch_env.py:427-485), which reads only the train's own new state
   unsigned long long done_bits = 0, malf_bits = 0, stopped_bits = 0, depart_bits = 0, active = 0;
   SFL_NU
-  for (int base = 0; base < T; base += G) {
+  for (int base = 0; base < Tw; base += G) {
     const int t = base + g.gl;
     int f_done = 0, f_malf = 0, f_stop = 0, f_dep = 0, f_act = 0;
     if (t < T) {
@@ -822,22 +833,23 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
     depart_bits |= (unsigned long long)g.ballot(f_dep) << base;
     active |= (unsigned long long)g.ballot(f_act) << base;
   }
-  const unsigned long long all_mask = T >= 64 ? ~0ull : ((1ull << T) - 1ull);
-  const int ended = done_bits == all_mask || now >= c_m.max_episode_steps;   // dones["__all__"] (Appendix B step 6)
+  const unsigned long long all_mask = Tw >= 64 ? ~0ull : ((1ull << Tw) - 1ull);
+  const int ended = live && (done_bits == all_mask || now >= c_m.max_episode_steps);   // dones["__all__"] (Appendix B step 6)
   const unsigned long long prev_done = R.done;
   // ---- phase D2: semaphores of done trains (switch_env.py:370-376); every train counts as done at the end
-  if ((done_bits & ~prev_done) || ended) {
-    g.sync();
+  const int release = (done_bits & ~prev_done) || ended;
+  if (g.wany(release)) {
+    const int NP = release ? c_L.NP : 0;
     SFL_NU
-    for (int p = g.gl; p < c_L.NP; p += G) {
+    for (int p = g.gl; p < NP; p += G) {
       int tr = e.sem()[p].z;
       if (tr >= 0 && (ended || ((done_bits >> tr) & 1))) e.sem()[p].z = -1;
     }
   }
   // ---- phase D3: departure bookings (switch_env.py:379-384), train order
-  if (depart_bits) {
+  if (g.wany(depart_bits != 0)) {
     g.sync();
-    if (g.gl == 0) {
+    if (depart_bits && g.gl == 0) {
       unsigned long long b = depart_bits;
       SFL_NU
       while (b) {
@@ -848,15 +860,16 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
     }
   }
   // ---- phase D4: extend_semaphores (rail_network.py:229-244)
-  if (stopped_bits) {
+  if (g.wany(stopped_bits != 0)) {
     g.sync();
+    const int NP = stopped_bits ? c_L.NP : 0;
     SFL_NU
-    for (int p = g.gl; p < c_L.NP; p += G) {
+    for (int p = g.gl; p < NP; p += G) {
       int4 r = e.sem()[p];
       if (r.z >= 0 && ((stopped_bits >> r.z) & 1)) { r.y = now + (r.y - r.x); r.x = now; e.sem()[p] = r; }
     }
     g.sync();
-    if (g.gl == 0) {
+    if (stopped_bits && g.gl == 0) {
       unsigned long long b = stopped_bits;
       SFL_NU
       while (b) {
@@ -869,7 +882,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
       }
     }
   }
-  if (g.gl == 0) {
+  if (live && g.gl == 0) {
     h->elapsed = now;
     const unsigned long long new_malf = malf_bits & ~R.malf_prev;
     if (new_malf) h->num_malf += popc64(new_malf);                       // switch_env.py:399-401
@@ -879,7 +892,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
     if (TRACE) { if (c_ra.trace_tick) h->n_tick_logged++; }
   }
   R.elapsed = now; R.ended = ended; R.active = active; R.done = done_bits; R.malf_prev = malf_bits;
-  R.ticks++; R.train_ticks += (unsigned long long)(T - popc64(prev_done));
+  if (live) { R.ticks++; R.train_ticks += (unsigned long long)(T - popc64(prev_done)); }
   g.sync();
 }
 
@@ -910,8 +923,10 @@ SFL_FN void episode_end(Env e, int env_id) {   // first lane
 template <int G, bool TRACE, bool TH>
 SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
   const Grp<G> g;
+  const int valid = env_id < c_ra.n_envs;                                 // idle slots of the last warp keep the warp's rendezvous
+  if (!valid) env_id = 0;
   char *gbase = c_ra.state + (size_t)env_id * c_L.env_stride;
-  const unsigned hot_bytes = c_ra.hot_bytes;
+  const unsigned hot_bytes = valid ? c_ra.hot_bytes : 0u;
   EnvT<TH> e;
   const sfl_hparams *hp;
   Scratch sc;
@@ -921,13 +936,15 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
     char *smem = g_smem + stage;
     SFL_NU
     for (unsigned o = g.gl * 16u; o < hot_bytes; o += G * 16u) *(int4 *)(smem + o) = *(const int4 *)(gbase + o);
-    SFL_NU
-    for (unsigned o = g.gl * 16u; o < (unsigned)sizeof(sfl_hparams); o += G * 16u)
-      *(int4 *)(smem + hot_bytes + o) = *(const int4 *)((const char *)(c_ra.hp + env_id) + o);
+    if (valid) {
+      SFL_NU
+      for (unsigned o = g.gl * 16u; o < (unsigned)sizeof(sfl_hparams); o += G * 16u)
+        *(int4 *)(smem + c_ra.hot_bytes + o) = *(const int4 *)((const char *)(c_ra.hp + env_id) + o);
+    }
     g.sync();
     e.hot = stage;
-    hp = (const sfl_hparams *)(smem + hot_bytes);
-    sc = make_scratch(smem + hot_bytes + (unsigned)sizeof(sfl_hparams), c_L.T);
+    hp = (const sfl_hparams *)(smem + c_ra.hot_bytes);
+    sc = make_scratch(smem + c_ra.hot_bytes + (unsigned)sizeof(sfl_hparams), c_L.T);
   }
 #else
   (void)stage;
@@ -937,15 +954,19 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
 #endif
   EnvHdr *h = e.h();
   TickRegs R;
-  R.elapsed = h->elapsed; R.ended = h->terminated | h->truncated; R.rng_blk = -1;
-  R.active = h->active_mask; R.done = h->done_mask; R.malf_prev = h->malf_prev_mask;
-  R.ticks = 0; R.train_ticks = 0;
-  int need_reset = h->need_reset, halted = h->halted;
+  R.elapsed = 0; R.ended = 0; R.rng_blk = -1; R.active = 0; R.done = 0; R.malf_prev = 0; R.ticks = 0; R.train_ticks = 0;
+  int need_reset = 0, live = 0;
+  if (valid) {
+    R.elapsed = h->elapsed; R.ended = h->terminated | h->truncated;
+    R.active = h->active_mask; R.done = h->done_mask; R.malf_prev = h->malf_prev_mask;
+    need_reset = h->need_reset; live = !h->halted;
+  }
   SFL_NU
   for (int it = 0; it < c_ra.max_ticks; it++) {
-    if (halted) break;
-    if (R.active || R.ended) {                                            // group-uniform: something is due before the tick
-      if (g.gl == 0) {
+    if (!g.wany(live)) break;                                             // warp-uniform
+    const int due = live && (R.active || R.ended);                        // something is due before the tick
+    if (g.wany(due)) {
+      if (due && g.gl == 0) {
         SFL_NU
         for (;;) {                                                        // agent_iter: FIFO in train-handle order
           if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<TRACE>(e, hp, env_id);
@@ -957,20 +978,19 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
         if (h->terminated || h->truncated) episode_end(e, env_id);
       }
       g.sync();
-      need_reset = h->need_reset;
-      R.active = 0;
+      if (due) { need_reset = h->need_reset; R.active = 0; }
     }
-    if (need_reset) {
-      if (hp->episodes >= 0 && h->episode >= hp->episodes) { halted = 1; break; }
-      env_reset<G>(e, g);
-      need_reset = 0;
-      R.elapsed = 0; R.ended = 0; R.rng_blk = -1; R.active = 0; R.done = 0; R.malf_prev = 0;
+    if (g.wany(live && need_reset)) {
+      if (live && need_reset && hp->episodes >= 0 && h->episode >= hp->episodes) live = 0;      // halt: need_reset stays set
+      const int on = live && need_reset;
+      env_reset<G>(e, g, on);
+      if (on) { need_reset = 0; R.elapsed = 0; R.ended = 0; R.rng_blk = -1; R.active = 0; R.done = 0; R.malf_prev = 0; }
     }
-    env_tick<G, TRACE>(e, sc, hp, env_id, g, R);
+    env_tick<G, TRACE>(e, sc, hp, env_id, g, R, live);
   }
   g.sync();
-  if (g.gl == 0) {
-    h->halted = halted;
+  if (valid && g.gl == 0) {
+    h->halted = !live;
     h->malf_prev_mask = R.malf_prev;
     h->ticks += R.ticks; h->train_ticks += R.train_ticks;
     sfl_env_counters *c = c_ra.counters + env_id;
