@@ -327,7 +327,7 @@ int sfl_create(const sfl_map_desc *map, const sfl_config *cfg, int device, void 
   {
     int g_trains = 1;
     while (g_trains < T && g_trains < 32) g_trains *= 2;
-    const long warps_wanted = (long)sm_count * 14;
+    const long warps_wanted = (long)sm_count * 13;                   // 2048 warps on 148 SMs qualify
     int g_warps = 1;
     while (g_warps < 32 && (long)cfg->n_envs * g_warps / 32 < warps_wanted) g_warps *= 2;
     int G = g_trains > g_warps ? g_trains : g_warps;

@@ -23,6 +23,8 @@
 #define SFL_NI __device__ __noinline__
 #define SFL_CONST __constant__
 #define SFL_NU _Pragma("unroll 1")
+#define SFL_U4 _Pragma("unroll 4")
+#define SFL_UA _Pragma("unroll")
 #else
 #define SFL_DEV 0
 #include <math.h>
@@ -31,6 +33,8 @@
 #define SFL_NI inline
 #define SFL_CONST static
 #define SFL_NU
+#define SFL_U4
+#define SFL_UA
 struct int4 { int x, y, z, w; };
 struct int2 { int x, y; };
 static inline int4 make_int4(int x, int y, int z, int w) { int4 r = {x, y, z, w}; return r; }
@@ -320,7 +324,7 @@ SFL_NI void q_update(Env e, const sfl_hparams *hp, unsigned key, int action, dou
       int A = c_m.sw[next_sw].y;
       mq = next_row[0];
       SFL_NU
-      for (int a = 1; a < A; a++) mq = next_row[a] > mq ? next_row[a] : mq;
+      for (int a = 1; a < A; a++) { const double v = next_row[a]; mq = v > mq ? v : mq; }
     }
     row[action] = dadd(dmul(one_m, q), dmul(lr, dadd(reward, dmul(hp->gamma, mq))));
   } else {
@@ -330,14 +334,16 @@ SFL_NI void q_update(Env e, const sfl_hparams *hp, unsigned key, int action, dou
 
 // distr_q.py:468-490 max_action
 SFL_FN int max_action(const double *row, int A, int mask) {
-  int best = 0;
+  int best = 0, b2 = -1;                       // first maximum over all actions / over the allowed ones (np.argmax)
+  double bv = row[0], b2v = 0.0;
+  if (mask & 1) { b2 = 0; b2v = bv; }
   SFL_NU
-  for (int a = 1; a < A; a++) if (row[a] > row[best]) best = a;
-  if ((mask >> best) & 1) return best;
-  int b2 = -1;
-  SFL_NU
-  for (int a = 0; a < A; a++) if (((mask >> a) & 1) && (b2 < 0 || row[a] > row[b2])) b2 = a;
-  return b2;
+  for (int a = 1; a < A; a++) {
+    const double v = row[a];
+    if (v > bv) { bv = v; best = a; }
+    if (((mask >> a) & 1) && (b2 < 0 || v > b2v)) { b2v = v; b2 = a; }
+  }
+  return ((mask >> best) & 1) ? best : b2;
 }
 
 // ------------------------------------------------------------------------------------------------ E3
@@ -723,9 +729,9 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
       if (wants) {
         SFL_NU
         for (int k = 0; k < T; k++) {
-          int2 o = *(const int2 *)&sc.tmp[k];
-          if (o.x == d) occ = k;                                         // k != t: my own src differs from my dst
-          if (o.y == d && o.y != o.x && k < t) blocked = 1;              // lowest handle wins a contended cell
+          const int2 o = *(const int2 *)&sc.tmp[k];
+          occ = o.x == d ? k : occ;                                      // k != t: my own src differs from my dst
+          blocked |= (o.y == d) & (o.y != o.x) & (k < t);                // lowest handle wins a contended cell
         }
         if (occ >= 0) { int2 o = *(const int2 *)&sc.tmp[occ]; if (o.y == s && o.y != o.x) blocked = 1; }   // swap
       }
