@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SFL_ABI_VERSION 2
+#define SFL_ABI_VERSION 3
 
 enum {
   SFL_OK = 0,
@@ -47,7 +47,10 @@ enum {
 enum {
   SFL_MODE_LEARN = 0,    /* distr_q.py:296-366  epsilon-greedy + Q-update (Philox instead of PCG64)  */
   SFL_MODE_GREEDY = 1,   /* distr_q.py:195-224  test(): max_action only, no update                   */
-  SFL_MODE_REPLAY = 2    /* learn() with the actions (and malfunction events) of a recorded trace    */
+  SFL_MODE_REPLAY = 2,   /* learn() with the actions (and malfunction events) of a recorded trace    */
+  SFL_MODE_STEP = 3      /* host-driven AEC protocol (switch_env.py:616-666): one launch applies the action the
+                            host chose for the waiting decision (replay_act[env * act_cap]), advances the trains to
+                            the next decision point and reports it in step_out; no learning on the device            */
 };
 
 /* Map + line + timetable constants, all HOST pointers; copied by sfl_create.
@@ -101,6 +104,7 @@ typedef struct sfl_sizes {
   uint64_t ep_log_bytes, ep_delay_bytes;
   uint64_t replay_act_bytes, replay_ev_bytes;
   uint64_t counters_bytes;      /* n_envs * sizeof(sfl_env_counters)                                  */
+  uint64_t step_out_bytes;      /* n_envs * sizeof(sfl_step_rec) (SFL_MODE_STEP only)                 */
   int32_t q_stride;             /* doubles per Q row (1 key slot + A_max)                             */
   int32_t a_max;
 } sfl_sizes;
@@ -110,6 +114,7 @@ typedef struct sfl_buffers {    /* all device pointers; optional ones may be NUL
   void *trace_dec; void *trace_tick; void *trace_sem;
   void *ep_log; void *ep_delay;
   void *replay_act; void *replay_ev;
+  void *step_out;
 } sfl_buffers;
 
 typedef struct sfl_env_counters {      /* written by sfl_run for every env                            */
@@ -125,6 +130,20 @@ typedef struct sfl_dec_rec {           /* one switch-agent decision (trace)     
   int32_t mask, action, next_sw, reward, done;
   uint64_t arrived;
 } sfl_dec_rec;
+
+/* SFL_MODE_STEP output per environment: what AECEnv.last() returns for the waiting decision (observer.py:246-308)
+ * plus what the previous ASyncSwitchEnv.step() returned (switch_env.py:663-666)                              */
+typedef struct sfl_step_rec {
+  int32_t pending;                     /* 1: (sw, train) waits for an action; 0: episode over (see done)             */
+  int32_t sw, train;
+  uint32_t key;                        /* dense state index of the observation                                        */
+  int32_t mask;                        /* action mask, bit a = action a allowed                                       */
+  int32_t done;                        /* terminated | truncated << 1                                                 */
+  int32_t elapsed;                     /* rail_env._elapsed_steps                                                     */
+  int32_t last_next_sw;                /* "next_switch" of the decision just applied, -1 if none                      */
+  uint64_t arrived;                    /* "arrived_trains" as a bit set                                               */
+  int32_t rewards[64];                 /* _cumulative_rewards[sw][train] for every train (switch_env.py:130, 289)     */
+} sfl_step_rec;
 
 typedef struct sfl_tick_rec { int32_t pos; int8_t dir, state; int16_t malf; } sfl_tick_rec;
 typedef struct sfl_ep_rec { double cum_reward; int32_t decisions, arrived, num_malfunctions, ticks; } sfl_ep_rec;

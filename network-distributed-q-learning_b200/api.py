@@ -24,6 +24,27 @@ import numpy as np
 from .backend import MODE_GREEDY, MODE_LEARN, Engine, RailMap
 
 
+class Discrete:
+    """gymnasium.spaces.Discrete as the reference uses it (switch_agents.py:204-259, distr_q.py:316-317):
+    ``n``, ``contains``, ``seed`` and ``sample(mask)`` = ``Generator(PCG64(seed)).choice(where(mask))``."""
+
+    def __init__(self, n: int):
+        self.n = int(n)
+        self._rng = np.random.default_rng()
+
+    def contains(self, x) -> bool:
+        return isinstance(x, (int, np.integer)) and 0 <= int(x) < self.n
+
+    def seed(self, seed=None):
+        self._rng = np.random.default_rng(seed)
+
+    def sample(self, mask=None) -> int:
+        if mask is None:
+            return int(self._rng.integers(self.n))
+        valid = np.where(np.asarray(mask) == 1)[0]
+        return int(self._rng.choice(valid)) if len(valid) else 0
+
+
 class MalfunctionParameters:
     """flatland.envs.malfunction_generators.MalfunctionParameters (main.py:28-32)."""
 
@@ -71,17 +92,105 @@ class ASyncSwitchEnv:
         self.rail_map = RailMap(rail_env.fixture)
         self.possible_agents = self.rail_map.tab.switch_names()          # switch_env.py:51-52
         self.agents = self.possible_agents
-        self.engine = Engine(self.rail_map, n_envs=self.n_envs, device=device, q_cap=q_cap, max_steps=max_steps, ep_cap=ep_cap,
-                             **(_engine_kwargs or {}))
+        kw = dict(act_cap=1)
+        kw.update(_engine_kwargs or {})
+        self.engine = Engine(self.rail_map, n_envs=self.n_envs, device=device, q_cap=q_cap, max_steps=max_steps, ep_cap=ep_cap, **kw)
         # the seven wall-clock accumulators main.py:72-78 prints (switch_env.py:67-73); the device loop has no
         # per-phase split, so the kernel time is booked on step_time and resets on reset_total_time
         self.flatland_step_time = self.step_time = self.last_time = 0.0
         self.action_selection_time = self.update_time = self.reset_time = self.reset_total_time = 0.0
         self.num_malfunctions = 0
         self.train_to_last_node: Dict[int, tuple] = {}
+        self._spaces: Dict[str, Discrete] = {}
+        self._rec = None
+        self._aec_hparams = None
+        self.view = 0
+        self.agent_selection, self.active_train = None, None
+        self.terminated = self.truncated = False
 
     def action_space_n(self, agent: str) -> int:
         return int(self.rail_map.tab.sw_A[self.agents.index(agent)])
+
+    def action_space(self, agent: str) -> Discrete:                       # switch_env.py:85-91
+        sp = self._spaces.get(agent)
+        if sp is None:
+            sp = self._spaces[agent] = Discrete(self.action_space_n(agent))
+        return sp
+
+    # ------------------------------------------------------------------ the AEC protocol, host-driven (switch_env.py:93-158, 616-678)
+    # One kernel launch per step(): the chosen action is applied on the device, the trains advance to the next decision
+    # point, and the next (switch, train) with its observation comes back.  With n_envs > 1 every call handles all
+    # environments in lockstep (``last_batch`` / ``step_batch``); the reference-shaped calls below address environment
+    # ``view`` (0) and need n_envs == 1 for ``step``.
+    def reset(self, seed=None, options=None):
+        eng = self.engine
+        if seed is not None:
+            self.seed = seed
+        base = 0 if self.seed is None else int(self.seed)
+        hp = self._aec_hparams or {}
+        eng.set_hparams(**hp, seeds=np.arange(self.n_envs, dtype=np.uint64) + np.uint64(base), episodes=1)
+        t0 = time.time()
+        eng.reset(keep_q=True, keep_interactions=True)
+        self._rec = eng.step(None)
+        self.reset_total_time += time.time() - t0
+        self._sync_view()
+
+    def _sync_view(self):
+        r = self._rec[self.view]
+        self.terminated, self.truncated = bool(r["done"] & 1), bool(r["done"] & 2)
+        self.rail_env._elapsed_steps = int(r["elapsed"])
+        self.agent_selection = self.agents[int(r["sw"])] if r["pending"] else None
+        self.active_train = int(r["train"]) if r["pending"] else None
+
+    def agent_iter(self, max_iter: int = 2 ** 63):                        # switch_env.py:616-622
+        n = 0
+        while self._rec is not None and self._rec[self.view]["pending"] and n < max_iter:
+            n += 1
+            self._sync_view()
+            yield self.agent_selection
+
+    def observe(self, agent=None) -> np.ndarray:                          # switch_env.py:668-678 -> observer.py:246-308
+        return np.array(self.rail_map.key_to_obs(int(self._rec[self.view]["key"])), dtype=np.int64)
+
+    def last(self, observe: bool = True):
+        """pettingzoo AECEnv.last(): (obs, rewards {train: float}, terminated, truncated, info)."""
+        r = self._rec[self.view]
+        T = self.rail_map.trains.T
+        if not r["pending"]:
+            return None, {h: 0.0 for h in range(T)}, self.terminated, self.truncated, {}
+        A = self.action_space_n(self.agent_selection)
+        mask = np.array([(int(r["mask"]) >> a) & 1 for a in range(A)], dtype=np.int8)
+        rewards = {h: float(r["rewards"][h]) for h in range(T)}
+        return (self.observe() if observe else None), rewards, self.terminated, self.truncated, \
+            {"action_mask": mask, "active_train": int(r["train"])}
+
+    def step(self, action):                                               # switch_env.py:632-666
+        if self.n_envs != 1:
+            raise RuntimeError("step() addresses one environment; use step_batch() with n_envs > 1")
+        r = self._rec[self.view]
+        if action is None or not r["pending"]:
+            return {}
+        if not self.action_space(self.agent_selection).contains(action):
+            raise AssertionError(f"invalid action {action} for {self.agent_selection}")        # switch_env.py:213-215
+        return self.step_batch([int(action)])[0]
+
+    def last_batch(self) -> np.ndarray:
+        """The per-environment ``sfl_step_rec`` array (pending, sw, train, key, mask, done, elapsed, rewards...)."""
+        return self._rec
+
+    def step_batch(self, actions):
+        t0 = time.time()
+        self._rec = self.engine.step(actions)
+        self.engine.check_errors(allow=1)
+        self.step_time += time.time() - t0
+        self._sync_view()
+        cells = self.rail_map.tab.switch_cells
+        out = []
+        for r in self._rec:
+            nxt = int(r["last_next_sw"])
+            out.append({"next_switch": tuple(int(x) for x in cells[nxt]) if nxt >= 0 else None,
+                        "arrived_trains": [h for h in range(self.rail_map.trains.T) if (int(r["arrived"]) >> h) & 1]})
+        return out
 
     def close(self):
         pass

@@ -21,7 +21,7 @@ from . import railmap
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libswitchfl_b200.so")
 
-MODE_LEARN, MODE_GREEDY, MODE_REPLAY = 0, 1, 2
+MODE_LEARN, MODE_GREEDY, MODE_REPLAY, MODE_STEP = 0, 1, 2, 3
 ERR_NO_TRAIN_AT_SWITCH = 1
 ERR_BITS = {1: "no train at active switch (observer.py:294-307)", 2: "infinite distance to target (observer.py:35-36)",
             4: "per-env Q table full (raise q_cap)", 8: "pending-update list full (raise pend_cap)",
@@ -49,12 +49,12 @@ class Config(C.Structure):
 class Sizes(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("state_bytes", "env_stride", "hparams_bytes", "trace_dec_bytes", "trace_tick_bytes",
                                           "trace_sem_bytes", "ep_log_bytes", "ep_delay_bytes", "replay_act_bytes",
-                                          "replay_ev_bytes", "counters_bytes")] + [("q_stride", C.c_int32), ("a_max", C.c_int32)]
+                                          "replay_ev_bytes", "counters_bytes", "step_out_bytes")] + [("q_stride", C.c_int32), ("a_max", C.c_int32)]
 
 
 class Buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("state", "hparams", "counters", "trace_dec", "trace_tick", "trace_sem", "ep_log",
-                                          "ep_delay", "replay_act", "replay_ev")]
+                                          "ep_delay", "replay_act", "replay_ev", "step_out")]
 
 
 HPARAMS_DT = np.dtype([("gamma", "f8"), ("epsilon", "f8"), ("epsilon_decay_rate", "f8"), ("lr", "f8"), ("lr_decay_rate", "f8"),
@@ -66,6 +66,8 @@ COUNTERS_DT = np.dtype([("decisions", "u8"), ("ticks", "u8"), ("train_ticks", "u
 DEC_DT = np.dtype([("ep", "i4"), ("tick", "i4"), ("sw", "i4"), ("train", "i4"), ("key", "u4"), ("mask", "i4"), ("action", "i4"),
                    ("next_sw", "i4"), ("reward", "i4"), ("done", "i4"), ("arrived", "u8")])
 TICK_DT = np.dtype([("pos", "i4"), ("dir", "i1"), ("state", "i1"), ("malf", "i2")])
+STEP_DT = np.dtype([("pending", "i4"), ("sw", "i4"), ("train", "i4"), ("key", "u4"), ("mask", "i4"), ("done", "i4"), ("elapsed", "i4"),
+                    ("last_next_sw", "i4"), ("arrived", "u8"), ("rewards", "i4", (64,))])
 EP_DT = np.dtype([("cum_reward", "f8"), ("decisions", "i4"), ("arrived", "i4"), ("num_malfunctions", "i4"), ("ticks", "i4")])
 assert HPARAMS_DT.itemsize == 80 and COUNTERS_DT.itemsize == 64 and DEC_DT.itemsize == 48 and TICK_DT.itemsize == 8 and EP_DT.itemsize == 24
 
@@ -89,7 +91,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sfl_total_decisions.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
     lib.sfl_export_q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.c_void_p]
     lib.sfl_import_q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_int, C.c_void_p]
-    if lib.sfl_abi_version() != 2:
+    if lib.sfl_abi_version() != 3:
         raise RuntimeError("switchfl_b200 ABI version mismatch")
     return lib
 
@@ -217,7 +219,7 @@ class Engine:
         self.buf = {"state": z(s.state_bytes), "hparams": z(s.hparams_bytes), "counters": z(s.counters_bytes),
                     "trace_dec": z(s.trace_dec_bytes), "trace_tick": z(s.trace_tick_bytes), "trace_sem": z(s.trace_sem_bytes),
                     "ep_log": z(s.ep_log_bytes), "ep_delay": z(s.ep_delay_bytes), "replay_act": z(s.replay_act_bytes),
-                    "replay_ev": z(s.replay_ev_bytes)}
+                    "replay_ev": z(s.replay_ev_bytes), "step_out": z(s.step_out_bytes)}
         b = Buffers(**{k: v.data_ptr() for k, v in self.buf.items()})
         self._ck(self.lib.sfl_bind(self.ctx, C.byref(b)))
         if lanes is not None:
@@ -295,12 +297,13 @@ class Engine:
     def run(self, mode: int, max_ticks: int):
         self._ck(self.lib.sfl_run(self.ctx, int(mode), int(max_ticks), self._stream()))
 
-    def set_replay(self, actions: Sequence[Sequence[int]], events: Optional[Sequence[np.ndarray]] = None):
+    def set_replay(self, actions: Optional[Sequence[Sequence[int]]], events: Optional[Sequence[np.ndarray]] = None):
         """actions[i]: the recorded action stream of env i; events[i]: int array [(tick, train, duration)]."""
-        a = np.full((self.n_envs, self.cfg.act_cap), -1, np.int8)
-        for i, s in enumerate(actions):
-            a[i, :len(s)] = s
-        self._upload("replay_act", a)
+        if actions is not None:
+            a = np.full((self.n_envs, self.cfg.act_cap), -1, np.int8)
+            for i, s in enumerate(actions):
+                a[i, :len(s)] = s
+            self._upload("replay_act", a)
         if self.cfg.ev_cap:
             ev = np.full((self.n_envs, self.cfg.ev_cap, 3), -1, np.int32)
             for i, e in enumerate(events or []):
@@ -308,6 +311,19 @@ class Engine:
                 e = e[np.lexsort((e[:, 1], e[:, 0]))] if len(e) else e
                 ev[i, :len(e)] = e
             self._upload("replay_ev", ev)
+
+    # ------------------------------------------------------------------ host-driven AEC protocol (SFL_MODE_STEP)
+    def step(self, actions: Optional[Sequence[int]] = None, max_ticks: Optional[int] = None) -> np.ndarray:
+        """Apply ``actions[i]`` to the decision waiting in env i (ignored where none waits), advance every env to
+        its next decision point and return the per-env ``sfl_step_rec`` array (what AECEnv.last() reports)."""
+        if self.cfg.act_cap < 1:
+            raise RuntimeError("Engine(act_cap >= 1) is needed for the step protocol")
+        a = np.full((self.n_envs, self.cfg.act_cap), -1, np.int8)
+        if actions is not None:
+            a[:, 0] = np.asarray(actions, np.int64).reshape(self.n_envs)
+        self._upload("replay_act", a)
+        self.run(MODE_STEP, int(self.map.fixture["max_episode_steps"]) + 2 if max_ticks is None else max_ticks)
+        return self._download("step_out", self.n_envs * STEP_DT.itemsize).view(STEP_DT).copy()
 
     # ------------------------------------------------------------------ results
     def total_decisions(self):

@@ -78,7 +78,7 @@ SFL_FN void env_init(const InitArgs &ia, int env_id, int lane, int lanes) {
     int q_rows = ia.keep_q ? e.h()->q_rows : 0;
     EnvHdr z;
     memset(&z, 0, sizeof(z));
-    z.need_reset = 1; z.pending_fin = -1; z.cur_dec = -1; z.q_rows = q_rows;
+    z.need_reset = 1; z.pending_fin = -1; z.cur_dec = -1; z.q_rows = q_rows; z.cur_train = -1; z.last_next_sw = -1;
     *e.h() = z;
   }
 }
@@ -206,6 +206,7 @@ int sfl_query_sizes(const sfl_map_desc *map, const sfl_config *cfg, sfl_sizes *o
   out->state_bytes = B * L.env_stride;
   out->hparams_bytes = B * sizeof(sfl_hparams);
   out->counters_bytes = B * sizeof(sfl_env_counters);
+  out->step_out_bytes = B * sizeof(sfl_step_rec);
   out->trace_dec_bytes = B * (uint64_t)cfg->dec_cap * sizeof(sfl_dec_rec);
   out->trace_tick_bytes = B * (uint64_t)cfg->tick_cap * map->T * sizeof(sfl_tick_rec);
   out->trace_sem_bytes = cfg->trace_sem ? B * (uint64_t)cfg->dec_cap * map->NP * 16ull : 0;
@@ -402,8 +403,10 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   Ctx *c = (Ctx *)ctx;
   if (!c) return fail(SFL_E_ARG, "null ctx%s");
   if (!c->bound) return fail(SFL_E_STATE, "sfl_bind first%s");
-  if (mode < SFL_MODE_LEARN || mode > SFL_MODE_REPLAY || max_ticks < 0) return fail(SFL_E_ARG, "bad mode / max_ticks%s");
-  if (mode == SFL_MODE_REPLAY && !c->bufs.replay_act) return fail(SFL_E_ARG, "replay mode needs replay_act%s");
+  if (mode < SFL_MODE_LEARN || mode > SFL_MODE_STEP || max_ticks < 0) return fail(SFL_E_ARG, "bad mode / max_ticks%s");
+  if ((mode == SFL_MODE_REPLAY || mode == SFL_MODE_STEP) && (!c->bufs.replay_act || c->cfg.act_cap < 1))
+    return fail(SFL_E_ARG, "replay / step mode needs replay_act (act_cap >= 1)%s");
+  if (mode == SFL_MODE_STEP && !c->bufs.step_out) return fail(SFL_E_ARG, "step mode needs step_out%s");
   RunArgs ra;
   memset(&ra, 0, sizeof(ra));
   ra.mode = mode; ra.max_ticks = max_ticks; ra.n_envs = c->cfg.n_envs; ra.trace_sem = c->cfg.trace_sem;
@@ -417,8 +420,10 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   ra.ep_log = c->cfg.ep_cap > 0 ? (sfl_ep_rec *)c->bufs.ep_log : nullptr;
   ra.ep_delay = c->cfg.ep_cap > 0 ? (int *)c->bufs.ep_delay : nullptr;
   ra.replay_act = (const int8_t *)c->bufs.replay_act;
-  ra.replay_ev = (mode == SFL_MODE_REPLAY && c->cfg.ev_cap > 0) ? (const int *)c->bufs.replay_ev : nullptr;
-  const int trace = ra.trace_dec || ra.trace_tick;
+  ra.step_out = (sfl_step_rec *)c->bufs.step_out;
+  // recorded malfunction events replace the Philox draws in replay mode, and in step mode when a schedule was bound
+  ra.replay_ev = ((mode == SFL_MODE_REPLAY || mode == SFL_MODE_STEP) && c->cfg.ev_cap > 0) ? (const int *)c->bufs.replay_ev : nullptr;
+  const int trace = ra.trace_dec || ra.trace_tick || mode == SFL_MODE_STEP;      // the step protocol lives in the trace kernels
 #ifndef SFL_HOST_EMUL
   const int G = c->lanes;
   int threads = SFL_CTA_THREADS;                       // shrink the CTA until its environments fit shared memory

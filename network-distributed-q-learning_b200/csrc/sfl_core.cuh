@@ -131,10 +131,11 @@ struct EnvHdr {            // 128 bytes at the start of every env block
   int terminated, truncated, need_reset, halted;
   int err, q_rows, pending_fin, cur_dec;
   int act_cursor, ev_cursor, n_dec_logged, n_tick_logged;
-  int n_ep_logged, q_init_on, aborted, pad1;
+  int n_ep_logged, q_init_on, aborted, cur_train;     // cur_train: SFL_MODE_STEP, the train whose decision waits for the host (-1: none)
   unsigned long long active_mask, malf_prev_mask, at_dest_mask, done_mask;
   unsigned long long decisions, ticks, train_ticks;
   double cum_reward;
+  int last_next_sw, pad2, pad3, pad4;  // last_next_sw: "next_switch" of the most recent decision (SFL_MODE_STEP)
 };
 
 // Per-train records (16 bytes each, one vector load per phase):
@@ -154,6 +155,7 @@ struct RunArgs {           // per-launch arguments
   sfl_env_counters *counters;
   sfl_dec_rec *trace_dec; sfl_tick_rec *trace_tick; int4 *trace_sem_buf;
   sfl_ep_rec *ep_log; int *ep_delay;
+  sfl_step_rec *step_out;
   const int8_t *replay_act; const int *replay_ev;     // ev: [env][ev_cap][3] = (tick, train, duration), tick-sorted, tick<0 ends
 };
 
@@ -405,7 +407,7 @@ SFL_FN int delay_at(Env e, int tgt_index, int cell, int dir, int now, int la) {
 template <bool TRACE, class Env>
 SFL_FN void finish_decision(Env e, const sfl_hparams *hp, int env_id) {
   EnvHdr *h = e.h();
-  if (c_ra.mode != SFL_MODE_GREEDY) {
+  if (c_ra.mode == SFL_MODE_LEARN || c_ra.mode == SFL_MODE_REPLAY) {
     unsigned long long fresh = h->done_mask & ~h->at_dest_mask;
     SFL_NU
     while (fresh) {
@@ -442,35 +444,30 @@ SFL_FN void finish_decision(Env e, const sfl_hparams *hp, int env_id) {
   }
 }
 
-// one switch-agent decision: observe (O1-O3) -> act (Q1) -> apply (E2, E3, R1) -> Q-update (Q2, Q3)
-template <bool TRACE, class Env>
-SFL_FN void decide(Env e, const sfl_hparams *hp, int env_id, int t) {
-  EnvHdr *h = e.h();
-  const int now = h->elapsed;
-  int4 ta = e.tra()[t], tb = e.trb()[t];
-  const int s = tb.y & 0xFFFF;
-  const int4 sw = c_m.sw[s];
-  const int P = sw.x, A = sw.y, p0 = sw.z, a0 = sw.w;
+// observation of train t at its active switch (observer.py:246-308 + switch_agents.py:104-134)
+struct Obs { int s, P, A, p0, a0, cur, semb, mask, ok; unsigned key; };
+template <class Env>
+SFL_FN Obs observe(Env e, int t, int now, const int4 ta, const int4 tb) {
+  Obs ob;
+  ob.s = tb.y & 0xFFFF;
+  const int4 sw = c_m.sw[ob.s];
+  ob.P = sw.x; ob.A = sw.y; ob.p0 = sw.z; ob.a0 = sw.w;
   const int4 tr0 = c_m.train0[t], tr1 = c_m.train1[t];
-  const int pos = ta.x, dir = ta.y & 0xFF, st = (ta.y >> 8) & 0xFF;
   const int my_port = (int)((unsigned)ta.w >> 16);
-  // ---- observe (observer.py:246-308)
   int semb = 0;
   SFL_NU
-  for (int k = 0; k < P; k++)
-    if (!port_blocked(e, c_m.port[p0 + k].x, p0 + k, t, now)) semb |= 1 << k;
-  int cur = my_port - p0;
-  if (cur < 0 || cur >= P) {
-    // observer.py:294-307: "No train detected at active switch" -- the reference then dies on an unbound current_port
-    // (:307).  There is nothing to be faithful to past this point: flag the env, abandon the episode, carry on.
-    h->err |= SFL_ERR_NO_TRAIN_AT_SWITCH; h->aborted++; h->truncated = 1;
-    return;
-  }
-  int delay = delay_at(e, tr0.w, pos, dir, now, tr1.y);
+  for (int k = 0; k < ob.P; k++)
+    if (!port_blocked(e, c_m.port[ob.p0 + k].x, ob.p0 + k, t, now)) semb |= 1 << k;
+  ob.semb = semb;
+  ob.cur = my_port - ob.p0;
+  ob.ok = ob.cur >= 0 && ob.cur < ob.P;
+  ob.key = 0u; ob.mask = 0;
+  if (!ob.ok) return ob;
+  int delay = delay_at(e, tr0.w, ta.x, ta.y & 0xFF, now, tr1.y);
   int level = delay <= 0 ? 0 : (delay <= (tr1.y - tr1.x) * 20 ? 1 : 2);           // observer.py:239-244
-  unsigned key = (((unsigned)(p0 + cur) * c_L.NT + tr0.w) * 16u + semb) * 3u + level;
-  const int4 px = c_m.pexit[p0 + cur];                                            // switch_agents.py:104-134
-  int mask = 1 << (A - 1);
+  ob.key = (((unsigned)(ob.p0 + ob.cur) * c_L.NT + tr0.w) * 16u + semb) * 3u + level;
+  const int4 px = c_m.pexit[ob.p0 + ob.cur];                                      // switch_agents.py:104-134
+  int mask = 1 << (ob.A - 1);
   {
     int ex[3] = {px.y, px.z, px.w};
 #if SFL_DEV
@@ -478,12 +475,35 @@ SFL_FN void decide(Env e, const sfl_hparams *hp, int env_id, int t) {
 #endif
     for (int i = 0; i < 3; i++) if (i < px.x && ((semb >> ((ex[i] >> 4) & 3)) & 1)) mask |= 1 << (ex[i] & 15);
   }
+  ob.mask = mask;
+  return ob;
+}
+
+// one switch-agent decision: observe (O1-O3) -> act (Q1) -> apply (E2, E3, R1) -> Q-update (Q2, Q3)
+template <bool TRACE, class Env>
+SFL_FN void decide(Env e, const sfl_hparams *hp, int env_id, int t) {
+  EnvHdr *h = e.h();
+  const int now = h->elapsed;
+  int4 ta = e.tra()[t], tb = e.trb()[t];
+  const Obs ob = observe(e, t, now, ta, tb);
+  if (!ob.ok) {
+    // observer.py:294-307: "No train detected at active switch" -- the reference then dies on an unbound current_port
+    // (:307).  There is nothing to be faithful to past this point: flag the env, abandon the episode, carry on.
+    h->err |= SFL_ERR_NO_TRAIN_AT_SWITCH; h->aborted++; h->truncated = 1;
+    return;
+  }
+  const int s = ob.s, A = ob.A, p0 = ob.p0, a0 = ob.a0, cur = ob.cur, mask = ob.mask;
+  const unsigned key = ob.key;
+  const int4 tr0 = c_m.train0[t], tr1 = c_m.train1[t];
+  const int pos = ta.x, dir = ta.y & 0xFF, st = (ta.y >> 8) & 0xFF;
+  const int my_port = (int)((unsigned)ta.w >> 16);
   const int reward_in = e.rewards()[s * c_L.T + t];                               // last(): _cumulative_rewards[agent][train]
   // ---- act (distr_q.py:312-320 / :211)
-  const int learning = c_ra.mode != SFL_MODE_GREEDY;
+  const int learning = c_ra.mode == SFL_MODE_LEARN || c_ra.mode == SFL_MODE_REPLAY;
   double *my_row = nullptr;
   int action = -1;
-  if (c_ra.mode == SFL_MODE_REPLAY) {
+  if (c_ra.mode == SFL_MODE_REPLAY || c_ra.mode == SFL_MODE_STEP) {
+    if (c_ra.mode == SFL_MODE_STEP) h->act_cursor = 0;         // the host's action for this decision
     if (h->act_cursor >= c_ra.act_cap) { h->err |= SFL_ERR_REPLAY_UNDERRUN; action = A - 1; }
     else action = c_ra.replay_act[(size_t)env_id * c_ra.act_cap + h->act_cursor++];
     if (action < 0 || action >= A) { h->err |= SFL_ERR_BAD_ACTION; action = A - 1; }
@@ -588,6 +608,7 @@ SFL_FN void decide(Env e, const sfl_hparams *hp, int env_id, int t) {
       h->n_dec_logged++;
     }
   }
+  if (TRACE) h->last_next_sw = next_switch;
   h->decisions++;
   h->pending_fin = s;
 }
@@ -926,6 +947,29 @@ SFL_FN void episode_end(Env e, int env_id) {   // first lane
 // [hot env state (hot_bytes) | sfl_hparams | Scratch].  The host build has no staging: it works on the env block itself.
 // One launch = max_ticks iterations; an iteration is one flatland tick preceded by every switch-agent decision that is
 // due (and by the end-of-episode bookkeeping + in-place reset when the episode is over).
+// ------------------------------------------------------------------------------------------------ SFL_MODE_STEP
+// The AEC protocol driven from the host (switch_env.py:616-666): report the waiting decision the way AECEnv.last()
+// would, or the end of the episode.  First lane of the group.
+template <class Env>
+SFL_FN void step_report(Env e, int env_id, int t) {
+  EnvHdr *h = e.h();
+  sfl_step_rec *o = c_ra.step_out + env_id;
+  o->pending = 0; o->sw = -1; o->train = -1; o->key = 0u; o->mask = 0;
+  if (t >= 0) {
+    const int4 ta = e.tra()[t], tb = e.trb()[t];
+    const Obs ob = observe(e, t, h->elapsed, ta, tb);
+    if (!ob.ok) { h->err |= SFL_ERR_NO_TRAIN_AT_SWITCH; h->aborted++; h->truncated = 1; }    // last() raises in the reference
+    else {
+      o->pending = 1; o->sw = ob.s; o->train = t; o->key = ob.key; o->mask = ob.mask;
+      SFL_NU
+      for (int k = 0; k < c_L.T; k++) o->rewards[k] = e.rewards()[ob.s * c_L.T + k];
+      h->cur_train = t;
+    }
+  }
+  o->done = h->terminated | (h->truncated << 1);
+  o->elapsed = h->elapsed; o->last_next_sw = h->last_next_sw; o->arrived = h->done_mask;
+}
+
 template <int G, bool TRACE, bool TH>
 SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
   const Grp<G> g;
@@ -967,12 +1011,28 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
     R.active = h->active_mask; R.done = h->done_mask; R.malf_prev = h->malf_prev_mask;
     need_reset = h->need_reset; live = !h->halted;
   }
+  const int stepping = TRACE && c_ra.mode == SFL_MODE_STEP;
+  int paused = 0;                                                         // stepping: a decision waits for the host
+  if (stepping) {
+    if (live && g.gl == 0) {
+      if (h->cur_train >= 0) { decide<TRACE>(e, hp, env_id, h->cur_train); h->cur_train = -1; }
+      else h->last_next_sw = -1;
+    }
+    g.sync();
+    if (live) R.ended = h->terminated | h->truncated;
+  }
   SFL_NU
   for (int it = 0; it < c_ra.max_ticks; it++) {
-    if (!g.wany(live)) break;                                             // warp-uniform
-    const int due = live && (R.active || R.ended);                        // something is due before the tick
+    if (!g.wany(live && !paused)) break;                                  // warp-uniform
+    const int due = live && !paused && (R.active || R.ended);             // something is due before the tick
     if (g.wany(due)) {
-      if (due && g.gl == 0) {
+      if (due && g.gl == 0 && stepping) {
+        if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<TRACE>(e, hp, env_id);
+        int t = -1;
+        if (!(h->terminated || h->truncated) && h->active_mask) { t = ffs64(h->active_mask); h->active_mask &= h->active_mask - 1; }
+        step_report(e, env_id, t);
+        if (h->terminated || h->truncated) episode_end(e, env_id);
+      } else if (due && g.gl == 0) {
         SFL_NU
         for (;;) {                                                        // agent_iter: FIFO in train-handle order
           if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<TRACE>(e, hp, env_id);
@@ -984,7 +1044,7 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
         if (h->terminated || h->truncated) episode_end(e, env_id);
       }
       g.sync();
-      if (due) { need_reset = h->need_reset; R.active = 0; }
+      if (due) { need_reset = h->need_reset; R.active = 0; if (stepping) paused = h->cur_train >= 0; }
     }
     if (g.wany(live && need_reset)) {
       if (live && need_reset && hp->episodes >= 0 && h->episode >= hp->episodes) live = 0;      // halt: need_reset stays set
@@ -992,7 +1052,7 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
       env_reset<G>(e, g, on);
       if (on) { need_reset = 0; R.elapsed = 0; R.ended = 0; R.rng_blk = -1; R.active = 0; R.done = 0; R.malf_prev = 0; }
     }
-    env_tick<G, TRACE>(e, sc, hp, env_id, g, R, live);
+    env_tick<G, TRACE>(e, sc, hp, env_id, g, R, live && !paused);
   }
   g.sync();
   if (valid && g.gl == 0) {

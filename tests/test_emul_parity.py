@@ -80,3 +80,92 @@ def test_emul_abandons_episode_exactly_where_the_reference_raises(emul_lib):
         assert np.array_equal(dec[k_mine][:n], np.array(o.trace[k_o])), k_mine
     assert np.array_equal(dec["reward"][:n].astype(np.float64), np.array(o.trace["dec_reward"]))
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------- the AEC protocol
+def _aec_env(name, emul_lib, n_envs=1):
+    """ASyncSwitchEnv on the host build, malfunction schedule of the golden bound as replay events."""
+    from switchfl_b200 import api
+    from tests._parity import golden_events
+    from tests._util import load_golden
+    fx, g = load_golden(name)
+    ev = golden_events(g)
+    env = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=n_envs, q_cap=64, ep_cap=2,
+                             _engine_kwargs={"_emul_lib": emul_lib, "ev_cap": len(ev) + 2})
+    env.engine.set_replay(None, [ev] * n_envs)
+    return env, g
+
+
+@pytest.mark.parametrize("name", ["loop_chord_7x7", "c1_synth18", "slips24_t6"])
+def test_emul_aec_protocol_matches_reference(name, emul_lib):
+    check_aec(*_aec_env(name, emul_lib))
+
+
+def check_aec(env, g):
+    """Drive reset / agent_iter / last / step exactly like distr_q.py:296-362 with the recorded actions: every
+    observation, mask, reward, next switch and arrival list must be the reference's -- and a host-side learner running
+    the reference's update rule on top of this env ends with the reference's Q-table."""
+    import numpy as np
+    from tests._util import hparams, q_dict
+    hp = hparams(g)
+    rm = env.rail_map
+    q = rm.q_init_rows(hp["default_q"])                                  # distr_q.py:299-300
+    n_act = {tuple(c): int(a) for c, a in zip(rm.tab.switch_cells, rm.tab.sw_A)}
+
+    def row(obs):
+        return q.setdefault(obs, [hp["default_q"]] * n_act[(obs[0], obs[1])])     # __check_entry, distr_q.py:47-57
+
+    ninter = {a: 0 for a in env.possible_agents}
+    i = 0
+    for ep in range(int(g["n_episodes"])):
+        env.reset(seed=int(g["seed"]))
+        update_dict, at_dest, cum = {}, [], 0.0
+        for agent in env.agent_iter():
+            obs, R, term, trunc, info = env.last()
+            assert not (term or trunc)
+            train = info["active_train"]
+            o = tuple(int(x) for x in obs)
+            assert o == tuple(int(x) for x in g["dec_obs"][i] if x != -9), (i, o)
+            assert list(info["action_mask"]) == [int(x) for x in g["dec_mask"][i] if x >= 0], i
+            reward = R[train]
+            assert reward == g["dec_reward"][i], i
+            assert env.rail_env._elapsed_steps == g["dec_tick"][i] and agent == env.possible_agents[int(g["dec_switch"][i])]
+            action = int(g["dec_action"][i])
+            post = env.step(action)
+            nxt = env.possible_agents.index("switch_%d-%d" % post["next_switch"])
+            assert nxt == g["dec_next_switch"][i], i
+            assert sum(1 << h for h in post["arrived_trains"]) == int(g["dec_arrived"][i]), i
+            this_sw = env.possible_agents.index(agent)
+            if (this_sw, train) in update_dict:                                                  # distr_q.py:329-338
+                pobs, pact, pagent = update_dict.pop((this_sw, train))
+                lr = hp["lr"] * hp["lr_decay_rate"] ** ninter[pagent]
+                r_ = row(pobs)
+                if agent != pagent:
+                    r_[pact] = (1 - lr) * r_[pact] + lr * (reward + hp["gamma"] * max(row(o)))
+                else:
+                    r_[pact] = (1 - lr) * r_[pact] + lr * reward
+            update_dict[(nxt, train)] = (o, action, agent)                                       # :340-342
+            for h in post["arrived_trains"]:                                                     # :345-356
+                if h not in at_dest:
+                    at_dest.append(h)
+                    for k in [k for k in update_dict if k[1] == h]:
+                        pobs, pact, pagent = update_dict.pop(k)
+                        lr = hp["lr"] * hp["lr_decay_rate"] ** ninter[pagent]
+                        r_ = row(pobs)
+                        r_[pact] = (1 - lr) * r_[pact] + lr * 1000.0
+            cum += reward
+            ninter[agent] += 1
+            i += 1
+        assert env.terminated or env.truncated
+        assert cum == g["ep_cum_reward"][ep]
+    assert i == len(g["dec_action"])
+    gq = q_dict(g["q_keys"], g["q_vals"])
+    exact = float(g["hp_lr_decay_rate"]) == 1.0
+    touched = {k: v for k, v in q.items()}
+    assert set(gq) <= set(touched) | set(gq)
+    for k, v in gq.items():
+        assert k in touched, k
+        if exact:
+            assert touched[k] == v, (k, touched[k], v)
+        else:
+            assert np.allclose(touched[k], v, rtol=1e-12, atol=0), (k, touched[k], v)

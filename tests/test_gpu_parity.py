@@ -105,3 +105,57 @@ def test_replay_underrun_is_reported_loudly():
     with pytest.raises(RuntimeError, match="replay action stream exhausted"):
         eng.check_errors()
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["c1_synth18", "slips24_t6"])
+def test_cuda_aec_protocol_matches_reference(name):
+    """reset / agent_iter / last / step through the CUDA path (SFL_MODE_STEP), driven like distr_q.py:296-362."""
+    from switchfl_b200 import api
+    from tests._parity import golden_events
+    from tests.test_emul_parity import check_aec
+    fx, g = load_golden(name)
+    ev = golden_events(g)
+    env = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=1, device="cuda:0", q_cap=64, ep_cap=2,
+                             _engine_kwargs={"ev_cap": len(ev) + 2})
+    env.engine.set_replay(None, [ev])
+    check_aec(env, g)
+    env.engine.close()
+
+
+def test_cuda_step_batch_lockstep_equals_single_env():
+    """Five environments stepped in lockstep with a random masked policy each: env i behaves exactly like a
+    single-environment run with the same seed and actions."""
+    from switchfl_b200 import api
+    fx, _ = load_golden("slips24_t6")
+    B = 5
+    env = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=B, device="cuda:0", q_cap=64, ep_cap=2)
+    env.reset(seed=100)
+    rng = np.random.default_rng(0)
+    logs = [[] for _ in range(B)]
+    for _ in range(4000):
+        rec = env.last_batch()
+        if not rec["pending"].any():
+            break
+        acts = np.full(B, -1)
+        for i in range(B):
+            if rec["pending"][i]:
+                allowed = [a for a in range(16) if (int(rec["mask"][i]) >> a) & 1]
+                acts[i] = rng.choice(allowed)
+                logs[i].append((int(rec["sw"][i]), int(rec["train"][i]), int(rec["key"][i]), int(rec["mask"][i]), int(acts[i]),
+                                int(rec["rewards"][i][rec["train"][i]])))
+        env.step_batch(acts)
+    assert all(len(l) > 10 for l in logs)
+    for i in (0, 3):
+        one = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=1, device="cuda:0", q_cap=64, ep_cap=2)
+        one.reset(seed=100 + i)
+        k = 0
+        for agent in one.agent_iter():
+            obs, R, term, trunc, info = one.last()
+            sw, train, key, mask, action, reward = logs[i][k]
+            assert agent == one.possible_agents[sw] and info["active_train"] == train and R[train] == reward
+            assert tuple(int(x) for x in obs) == one.rail_map.key_to_obs(key)
+            one.step(action)
+            k += 1
+        assert k == len(logs[i])
+        one.engine.close()
+    env.engine.close()

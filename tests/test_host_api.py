@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol(product_lib):
     assert {"sfl_create", "sfl_run", "sfl_reset", "sfl_bind", "sfl_export_q", "sfl_import_q", "sfl_query_sizes"} <= set(names)
     for n in names:
         assert hasattr(product_lib, n), f"{n} declared in include/switchfl_b200.h but not exported"
-    assert product_lib.sfl_abi_version() == 2
+    assert product_lib.sfl_abi_version() == 3
 
 
 def test_struct_layouts_match_the_header():
@@ -48,8 +48,8 @@ def test_struct_layouts_match_the_header():
 #include <stdio.h>
 #include "switchfl_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(sfl_map_desc), sizeof(sfl_config), sizeof(sfl_hparams), sizeof(sfl_sizes),
-         sizeof(sfl_buffers), sizeof(sfl_env_counters), sizeof(sfl_dec_rec), sizeof(sfl_tick_rec), sizeof(sfl_ep_rec));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(sfl_map_desc), sizeof(sfl_config), sizeof(sfl_hparams), sizeof(sfl_sizes),
+         sizeof(sfl_buffers), sizeof(sfl_env_counters), sizeof(sfl_dec_rec), sizeof(sfl_tick_rec), sizeof(sfl_ep_rec), sizeof(sfl_step_rec));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as tmp:
@@ -58,7 +58,7 @@ int main(void) {
         got = [int(x) for x in subprocess.check_output([os.path.join(tmp, "s")]).split()]
     want = [C.sizeof(backend.MapDesc), C.sizeof(backend.Config), backend.HPARAMS_DT.itemsize, C.sizeof(backend.Sizes),
             C.sizeof(backend.Buffers), backend.COUNTERS_DT.itemsize, backend.DEC_DT.itemsize, backend.TICK_DT.itemsize,
-            backend.EP_DT.itemsize]
+            backend.EP_DT.itemsize, backend.STEP_DT.itemsize]
     assert got == want
 
 
