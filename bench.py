@@ -38,6 +38,10 @@ SEED = 450565
 WORKLOADS = {
     "c2": ("c1_synth18", 4096, 1024,
            "C2: 4096 lockstep envs of the test_model.py map (c1_synth18 stand-in), distributed Q-learning, learn mode"),
+    "c3": ("@c3", 5120, 8192,
+           "C3: hyperparam_tuning.py default grid (eps .5, decay .9997, lr .1) x seeds {64,65,66,67,69} = 5 maps (80x80, 15 trains, "
+           "25 cities, no malfunctions; synthetic stand-ins), each (map, point) replicated with distinct RNG streams: "
+           "5 x 1024 envs per GPU, distributed Q-learning, learn mode"),
     "c4": ("c4_synth100_t50", 8192, 8192,
            "C4: large synthetic map (100x100, 50 trains, 281 switches, malfunctions), 65536 envs per 8 GPUs = 8192 per GPU, "
            "distributed Q-learning, learn mode"),
@@ -49,10 +53,22 @@ WORKLOAD = WORKLOADS["c2"][3]
 def select_workload(args):
     global FIXTURE, WORKLOAD
     name, envs, q_cap, desc = WORKLOADS[args.workload]
-    FIXTURE = os.path.join(ROOT, "tests", "golden", name + ".fixture.npz")
+    FIXTURE = name if name.startswith("@") else os.path.join(ROOT, "tests", "golden", name + ".fixture.npz")
     WORKLOAD = desc if not args.envs or args.envs == envs else desc + f" [envs per GPU overridden: {args.envs}]"
     args.envs = args.envs or envs
     args.q_cap = args.q_cap or q_cap
+
+
+C3_SEEDS = (64, 65, 66, 67, 69)                                          # hyperparam_tuning.py:10
+
+
+def workload_fixtures():
+    """The maps of the selected workload: one for C2 / C4, the five seed maps of the hyper-parameter grid for C3."""
+    from switchfl_b200 import mapgen
+    if FIXTURE == "@c3":                                                  # hyperparam_tuning.py:17-26, synthetic stand-ins
+        return [mapgen.make_fixture(n=80, n_trains=15, n_chords=50, seed=s, num_cities=25, name=f"c3_synth80_s{s}", p_slip=0.3)
+                for s in C3_SEEDS]
+    return [mapgen.load_fixture(FIXTURE)]
 
 
 def bytes_per_decision(k_bar: float, P: float, A: float, A2: float) -> float:
@@ -127,7 +143,8 @@ def _cpu_worker(args):
     load_package()
     from switchfl_b200 import backend, mapgen
     from oracle.switchfl_oracle import SwitchFLOracle
-    fx = mapgen.load_fixture(FIXTURE)
+    fxs = workload_fixtures()
+    fx = fxs[seed % len(fxs)]
     rm = backend.RailMap(fx)
     o = SwitchFLOracle(fx, rm.tab, seed=seed, **HP)
     rng = np.random.default_rng(seed)
@@ -200,28 +217,42 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = f"cuda:{local}"
-    fx = mapgen.load_fixture(FIXTURE)
+    fxs = workload_fixtures()
     B = args.envs
-    seeds = np.arange(B, dtype=np.uint64) + np.uint64(SEED + rank * B)
+    parts = len(fxs)
+    Bp = B // parts                                                       # environments per map
+    B = Bp * parts
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident arm: Engine level, CUDA-event timed
-    rm = backend.RailMap(fx)
-    eng = backend.Engine(rm, n_envs=B, device=dev, q_cap=args.q_cap, ep_cap=4, lanes=args.lanes or None)
-    lanes = eng.lanes
-    eng.set_hparams(**HP, seeds=seeds, episodes=-1)
-    eng.reset()
-    eng.enable_q_init(True)
+    def seeds_of(k):
+        return np.arange(Bp, dtype=np.uint64) + np.uint64(SEED + rank * B + k * Bp)
+
+    # ---------------- device-resident arm: Engine level, CUDA-event timed (one engine per map, one stream)
+    rms = [backend.RailMap(fx) for fx in fxs]
+    engs = [backend.Engine(rm, n_envs=Bp, device=dev, q_cap=args.q_cap, ep_cap=4, lanes=args.lanes or None) for rm in rms]
+    lanes = engs[0].lanes
+    for k, eng in enumerate(engs):
+        eng.set_hparams(**HP, seeds=seeds_of(k), episodes=-1)
+        eng.reset()
+        eng.enable_q_init(True)
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
-        eng.run(backend.MODE_LEARN, args.ticks)
+        for eng in engs:
+            eng.run(backend.MODE_LEARN, args.ticks)
     barrier()
-    d0, t0 = eng.total_decisions()
-    tt0 = int(eng.counters()["train_ticks"].sum())
+
+    def totals():
+        d = t = tt = 0
+        for eng in engs:
+            a, b_ = eng.total_decisions()
+            d += a; t += b_; tt += int(eng.counters()["train_ticks"].sum())
+        return d, t, tt
+
+    d0, t0, tt0 = totals()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     wall0 = time.time()
@@ -229,45 +260,52 @@ def run_ours(args):
     start.record()
     for a, b in evs:
         a.record()
-        eng.run(backend.MODE_LEARN, args.ticks)
+        for eng in engs:
+            eng.run(backend.MODE_LEARN, args.ticks)
         b.record()
     stop.record()
     barrier()
     if sampler:
         sampler.mark(wall0, time.time())
     ms = start.elapsed_time(stop)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    d1, t1 = eng.total_decisions()
-    tt1 = int(eng.counters()["train_ticks"].sum())
-    # On congested maps the reference itself dies in observer.py:294-307 ("No train detected at active switch");
-    # the kernel abandons such an episode and resets the env.  Every other error bit is fatal here.
-    eng.check_errors(allow=backend.ERR_NO_TRAIN_AT_SWITCH)
-    cn = eng.counters()
-    episodes, aborted = int(cn["episodes"].sum()), int(cn["aborted"].sum())
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs])) / parts            # mean duration of ONE k_run launch
+    d1, t1, tt1 = totals()
+    episodes = aborted = q_rows_max = 0
+    state_mb = 0.0
+    for eng in engs:
+        # On congested maps the reference itself dies in observer.py:294-307 ("No train detected at active switch");
+        # the kernel abandons such an episode and resets the env.  Every other error bit is fatal here.
+        eng.check_errors(allow=backend.ERR_NO_TRAIN_AT_SWITCH)
+        cn = eng.counters()
+        episodes += int(cn["episodes"].sum()); aborted += int(cn["aborted"].sum())
+        q_rows_max = max(q_rows_max, int(cn["q_rows"].max()))
+        state_mb += eng.sizes.state_bytes / 1e6
+        eng.close()
     dec, ticks, train_ticks = d1 - d0, t1 - t0, tt1 - tt0
-    state_mb = eng.sizes.state_bytes / 1e6
-    eng.close()
-    del eng
+    del engs
     torch.cuda.empty_cache()
 
     # ---------------- end-to-end arm: public API, host buffers in the timed region
-    env = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=B, device=dev, q_cap=args.q_cap, ep_cap=4,
-                             _engine_kwargs={"lanes": args.lanes or None})
-    model = api.DistrQLearning(env=env, seed=SEED + rank * B, **HP)
+    models = []
+    for k, fx in enumerate(fxs):
+        env = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=Bp, device=dev, q_cap=args.q_cap, ep_cap=4,
+                                 _engine_kwargs={"lanes": args.lanes or None})
+        models.append(api.DistrQLearning(env=env, seeds=seeds_of(k), **HP))
     for _ in range(args.warmup):
-        model.learn_chunk(args.ticks)
+        for m in models:
+            m.learn_chunk(args.ticks)
     barrier()
-    c0 = model.learn_chunk(0)["decisions"].sum()
+    c0 = sum(int(m.learn_chunk(0)["decisions"].sum()) for m in models)
     barrier()
     w0 = time.perf_counter()
     for _ in range(args.steps):
-        c = model.learn_chunk(args.ticks)
+        cs = [m.learn_chunk(args.ticks) for m in models]
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - w0
-    e2e_dec = int(c["decisions"].sum() - c0)
+    e2e_dec = sum(int(c["decisions"].sum()) for c in cs) - c0
     clocks = sampler.stop() if sampler else None
-    h2d = int(env.engine.sizes.hparams_bytes)
-    d2h = int(env.engine.sizes.counters_bytes)
+    h2d = sum(int(m.env.engine.sizes.hparams_bytes) for m in models)
+    d2h = sum(int(m.env.engine.sizes.counters_bytes) for m in models)
 
     # ---------------- reduce over ranks: max time, summed work
     if dist is not None:
@@ -283,14 +321,14 @@ def run_ours(args):
         return
     value = dec / (ms / 1000.0)
     k_bar = train_ticks / max(dec, 1)
-    P = float(np.mean(rm.tab.sw_P)); A = float(np.mean(rm.tab.sw_A))
+    P = float(np.mean(np.concatenate([rm.tab.sw_P for rm in rms]))); A = float(np.mean(np.concatenate([rm.tab.sw_A for rm in rms])))
     bpd = bytes_per_decision(k_bar, P, A, A)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    per_gpu_dec_per_launch = dec / world / args.steps
+    per_gpu_dec_per_launch = dec / world / args.steps / parts
     achieved = per_gpu_dec_per_launch * bpd / (kern_ms / 1000.0) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -301,16 +339,16 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_envs_per_gpu": B, "ticks_per_step": args.ticks, "q_cap": args.q_cap, "lanes_per_env": lanes,
+            "config": {"workload": WORKLOAD, "n_envs_per_gpu": B, "maps": parts, "ticks_per_step": args.ticks, "q_cap": args.q_cap, "lanes_per_env": lanes,
                        "train_ticks_per_decision": k_bar, "ticks": ticks, "episodes_rank0": episodes,
-                       "episodes_abandoned_rank0": aborted,
+                       "episodes_abandoned_rank0": aborted, "q_rows_max_rank0": q_rows_max,
                        "l2": f"inputs larger than L2: {state_mb:.0f} MB of env state + Q tables per GPU vs 126 MB L2",
                        "sharding": "envs by seed range, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_run", "bytes_per_decision": bpd, "kernel_ms": kern_ms, "peak_source": peak_src,
                          "note": "per-env decision chains are serial: latency/issue-bound, not HBM-bound (SURVEY 8d honest note)"},
             "e2e": {"value": e2e_dec / e2e_s, "unit": "decisions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps, "clocks": clocks}
+            "gpu_launches": args.steps * parts, "clocks": clocks}
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         d, busy, wall, eps = cpu_sample(args.cpu_seconds, cores)

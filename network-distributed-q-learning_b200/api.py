@@ -238,8 +238,8 @@ class DistrQLearning:
     def _apply_q_init_to_existing_rows(self):
         """distr_q.py:156-158,179-181 ASSIGN the initial rows at t == 0, overwriting whatever load()/test() put there."""
         eng = self.env.engine
-        init_rows = self.env.rail_map.q_init_rows(self.default_q)
         for i in range(self.env.n_envs):
+            init_rows = self.env.rail_map.q_init_rows(self._default_q_of(i))
             q = eng.export_q(i)
             hit = [k for k in q if k in init_rows]
             if hit:
@@ -310,7 +310,7 @@ class DistrQLearning:
                 cum_reward_exploit.append(r)
                 arrived_exploit.append(a)
             if checkpoint_freq and (cut + 1) % checkpoint_freq == 0 and out_dir:
-                self.q_table = eng.export_q(p, include_init=self._q_inited, default_q=self.default_q)
+                self.q_table = eng.export_q(p, include_init=self._q_inited, default_q=self._default_q_of(p))
                 self.save(os.path.join(out_dir, f"checkpoint_{cut + 1}.pkl"))
                 np.savez_compressed(os.path.join(out_dir, f"cum_reward_checkpoint_{cut + 1}.npz"), x=cum_reward[p])
                 np.savez_compressed(os.path.join(out_dir, f"arrived_trains_checkpoint_{cut + 1}.npz"), x=arrived[p, :cut])
@@ -318,24 +318,39 @@ class DistrQLearning:
                 np.savez_compressed(os.path.join(out_dir, f"trains_at_dest_checkpoint_{cut + 1}.npz"), x=[])
                 np.savez_compressed(os.path.join(out_dir, f"num_malfunctions_checkpoint_{cut + 1}.npz"), x=num_malf[p, :cut])
         self._table_dirty = True
-        self.q_table = eng.export_q(p, include_init=self._q_inited, default_q=self.default_q)
+        self.q_table = eng.export_q(p, include_init=self._q_inited, default_q=self._default_q_of(p))
         self.metrics = dict(cum_reward=cum_reward, arrived_trains=arrived, delays=delays, num_malfunctions=num_malf,
                             cum_reward_exploit=np.array(cum_reward_exploit), arrived_trains_exploit=np.array(arrived_exploit),
                             wall_s=time.time() - t_start)
         if out_dir:
-            np.savez_compressed(os.path.join(out_dir, "cum_reward.npz"), x=cum_reward[p])
-            np.savez_compressed(os.path.join(out_dir, "arrived_trains.npz"), x=arrived[p])
-            np.savez_compressed(os.path.join(out_dir, "delays.npz"), x=delays[p])
-            np.savez_compressed(os.path.join(out_dir, "num_malfunctions.npz"), x=num_malf[p])
-            if exploit_freq is not None:
-                np.savez_compressed(os.path.join(out_dir, "cum_reward_exploit.npz"), x=[r[p] for r in cum_reward_exploit])
-                np.savez_compressed(os.path.join(out_dir, "arrived_trains_exploit.npz"), x=[a[p] for a in arrived_exploit])
+            self.write_outputs(p, out_dir, exploit=exploit_freq is not None, pkl=False)
             np.savez_compressed(os.path.join(out_dir, "batched_metrics.npz"), cum_reward=cum_reward, arrived_trains=arrived,
                                 delays=delays, num_malfunctions=num_malf, seeds=self.seeds)
         if num_episodes:
             env.num_malfunctions = int(num_malf[p, -1])
             env.train_to_last_node = {h: (None, float(delays[p, -1, h])) for h in range(T)}
         env.close()
+
+    def _default_q_of(self, i: int) -> float:
+        d = np.asarray(self.default_q, np.float64).reshape(-1)
+        return float(d[i % d.size])
+
+    def write_outputs(self, env_index: int, out_dir: str, exploit: bool = True, pkl: bool = True):
+        """The reference's end-of-learn files (distr_q.py:368-375, main.py:66) for environment ``env_index``."""
+        m, i = self.metrics, env_index
+        os.makedirs(out_dir, exist_ok=True)
+        np.savez_compressed(os.path.join(out_dir, "cum_reward.npz"), x=m["cum_reward"][i])
+        np.savez_compressed(os.path.join(out_dir, "arrived_trains.npz"), x=m["arrived_trains"][i])
+        np.savez_compressed(os.path.join(out_dir, "delays.npz"), x=m["delays"][i])
+        np.savez_compressed(os.path.join(out_dir, "num_malfunctions.npz"), x=m["num_malfunctions"][i])
+        if exploit:
+            np.savez_compressed(os.path.join(out_dir, "cum_reward_exploit.npz"), x=[r[i] for r in m["cum_reward_exploit"]])
+            np.savez_compressed(os.path.join(out_dir, "arrived_trains_exploit.npz"), x=[a[i] for a in m["arrived_trains_exploit"]])
+        if pkl:
+            keep = self.q_table
+            self.q_table = self.env.engine.export_q(i, include_init=self._q_inited, default_q=self._default_q_of(i))
+            self.save(os.path.join(out_dir, "distr_q_model.pkl"))
+            self.q_table = keep
 
     # ------------------------------------------------------------------ distr_q.py:184-241
     def test(self, out_dir, plot=False, save_outputs=True, _batched=False):
@@ -362,7 +377,7 @@ class DistrQLearning:
                 np.savez_compressed(os.path.join(out_dir, "delays.npz"), x=list(delays[p]))
         if _batched:
             return cum, arr, delays
-        self.q_table = eng.export_q(p, include_init=self._q_inited, default_q=self.default_q)   # test() inserts rows (App. A #15)
+        self.q_table = eng.export_q(p, include_init=self._q_inited, default_q=self._default_q_of(p))   # test() inserts rows (App. A #15)
         return float(cum[p]), int(arr[p]), list(delays[p])
 
     # ------------------------------------------------------------------ distr_q.py:492-527

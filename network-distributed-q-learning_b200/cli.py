@@ -1,0 +1,123 @@
+"""The reference's driver scripts on the batched backend.
+
+    python -m switchfl_b200.cli -c config.ini                 # main.py:83-88, same INI schema
+    launch_grid(hyperparams, random_seeds, out_dir, ...)      # hyperparam_tuning.py:42-91 without the process fan-out
+
+``config.ini`` keeps the reference's sections and keys (hyperparam_tuning.py:51-78): MISC{random_seed, out_dir,
+checkpoint_freq, exploit_freq}, ENV{width, height, max_num_cities, max_rails_between_cities, max_rail_pairs_in_city,
+number_of_agents, malfunction_rate, min_duration, max_duration}, MODEL{gamma, epsilon, epsilon_decay_rate, lr,
+lr_decay_rate, default_q, num_episodes}.  Two optional keys are new: ENV.fixture (a map fixture .npz recorded from
+flatland, see tools/record_flatland_fixture.py) and MISC.n_envs (lockstep replicas with seeds random_seed + i).
+Without ENV.fixture the map comes from the synthetic generator with the same size / train count / seed, because
+flatland's sparse_rail_generator cannot run here (mapgen.py).
+"""
+from __future__ import annotations
+
+import argparse
+import configparser
+import os
+import time
+from itertools import product
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import mapgen, sharding
+from .api import ASyncSwitchEnv, DistrQLearning, MalfunctionParameters, ParamMalfunctionGen, RailEnv
+
+
+def fixture_from_env_section(env: Dict[str, str], seed: int) -> dict:
+    if env.get("fixture"):
+        return mapgen.load_fixture(env["fixture"])
+    n = int(env["width"])
+    if int(env["height"]) != n:
+        raise ValueError("the reference only works on square grids (utils/rail_graph.py:43-48)")
+    cities = int(env.get("max_num_cities", 2))
+    chords = max(2, cities * int(env.get("max_rails_between_cities", 1)) * int(env.get("max_rail_pairs_in_city", 1)) // 2)
+    return mapgen.make_fixture(n=n, n_trains=int(env["number_of_agents"]), n_chords=chords, seed=seed, num_cities=cities)
+
+
+def launch_experiment(config_path: str, device: str = "cuda:0", _engine_kwargs=None) -> DistrQLearning:
+    """main.py:13-78."""
+    start_time = time.time()
+    config = configparser.ConfigParser()
+    config.read(config_path)
+    misc, envs, mdl = config["MISC"], config["ENV"], config["MODEL"]
+    out_dir = misc["out_dir"]
+    seed = int(misc["random_seed"])
+    mf = ParamMalfunctionGen(MalfunctionParameters(malfunction_rate=float(envs["malfunction_rate"]),
+                                                   min_duration=int(envs["min_duration"]), max_duration=int(envs["max_duration"])))
+    rail_env = RailEnv(fixture_from_env_section(dict(envs), seed), malfunction_generator=mf)
+    env = ASyncSwitchEnv(rail_env, render_mode=None, max_steps=100_000, n_envs=int(misc.get("n_envs", 1)), device=device,
+                         _engine_kwargs=_engine_kwargs)
+    model = DistrQLearning(env=env, gamma=float(mdl["gamma"]), epsilon=float(mdl["epsilon"]),
+                           epsilon_decay_rate=float(mdl["epsilon_decay_rate"]), lr=float(mdl["lr"]),
+                           lr_decay_rate=float(mdl["lr_decay_rate"]), default_q=float(mdl["default_q"]), seed=seed)
+    num_episodes = int(mdl["num_episodes"])
+    model.learn(num_episodes=num_episodes, out_dir=out_dir, checkpoint_freq=int(misc["checkpoint_freq"]),
+                exploit_freq=int(misc["exploit_freq"]))
+    model.save(os.path.join(out_dir, "distr_q_model.pkl"))
+    elapsed_time = time.time() - start_time
+    print("DONE!")                                                       # main.py:68-78
+    print(f"TOTAL TIME: {elapsed_time:.1f} seconds")
+    print(f"Seconds per episode: {elapsed_time / max(num_episodes, 1):.1f}")
+    print(f"Flatland step time: {env.flatland_step_time:.1f} seconds")
+    print(f"Total step time: {env.step_time:.1f} seconds")
+    print(f"Total last time: {env.last_time:.1f} seconds")
+    print(f"Action selection time: {env.action_selection_time:.1f} seconds")
+    print(f"Update time: {env.update_time:.1f} seconds")
+    print(f"Flatland reset time: {env.reset_time:.1f} seconds")
+    print(f"Total reset time: {env.reset_total_time:.1f} seconds")
+    return model
+
+
+def launch_grid(hyperparams: Dict[str, Sequence[float]], random_seeds: Sequence[int], out_dir: str, env_section: Dict[str, object],
+                num_episodes: int, checkpoint_freq: int, exploit_freq: Optional[int], gamma: float = 1.0, default_q: float = 0.0,
+                device: str = "cuda:0", _engine_kwargs=None) -> List[str]:
+    """hyperparam_tuning.py:42-91: every (grid point, seed) pair gets ``out_dir/exp_i/seed_j/`` with its config.ini
+    and the reference's output files.  One seed = one map (the generators are seeded with it), so each seed is ONE
+    batched engine whose environments are the grid points; under torchrun the seeds are sharded over the ranks."""
+    names = list(hyperparams)
+    points = [dict(zip(names, v)) for v in product(*[hyperparams[n] for n in names])]
+    rank, world_size, _ = sharding.world()
+    lo, hi = sharding.shard_range(len(random_seeds), rank, world_size)
+    written = []
+    for rdx in range(lo, hi):
+        seed = int(random_seeds[rdx])
+        fx = fixture_from_env_section({k: str(v) for k, v in env_section.items()}, seed)
+        mf = ParamMalfunctionGen(MalfunctionParameters(float(env_section.get("malfunction_rate", 0.0)),
+                                                       int(env_section.get("min_duration", 0)), int(env_section.get("max_duration", 0))))
+        env = ASyncSwitchEnv(RailEnv(fx, malfunction_generator=mf), render_mode=None, max_steps=100_000, n_envs=len(points),
+                             device=device, _engine_kwargs=_engine_kwargs)
+        col = lambda k, d: np.array([p.get(k, d) for p in points], np.float64)
+        model = DistrQLearning(env=env, gamma=gamma, epsilon=col("epsilon", 0.4), epsilon_decay_rate=col("epsilon_decay_rate", 0.0),
+                               lr=col("lr", 0.4), lr_decay_rate=col("lr_decay_rate", 0.0), default_q=default_q,
+                               seeds=np.full(len(points), seed, np.uint64))          # same seed for every point, as the reference
+        model.learn(num_episodes=num_episodes, out_dir=None, checkpoint_freq=checkpoint_freq, exploit_freq=exploit_freq)
+        for idx, params in enumerate(points):
+            exp_dir = os.path.join(out_dir, f"exp_{idx}", f"seed_{rdx}")
+            os.makedirs(exp_dir, exist_ok=True)
+            config = configparser.ConfigParser()
+            config["MISC"] = {"random_seed": str(seed), "out_dir": exp_dir, "checkpoint_freq": str(checkpoint_freq),
+                              "exploit_freq": str(exploit_freq)}
+            config["ENV"] = {k: str(v) for k, v in env_section.items()}
+            config["MODEL"] = {"gamma": str(gamma), **{k: str(params[k]) for k in names}, "default_q": str(default_q),
+                               "num_episodes": str(num_episodes)}
+            with open(os.path.join(exp_dir, "config.ini"), "w") as f:
+                config.write(f)
+            model.write_outputs(idx, exp_dir, exploit=exploit_freq is not None)
+            written.append(exp_dir)
+        env.engine.close()
+    return written
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-c", "--config", type=str, help="Config file path", required=True)
+    ap.add_argument("--device", default="cuda:0")
+    args = ap.parse_args(argv)
+    launch_experiment(args.config, device=args.device)
+
+
+if __name__ == "__main__":
+    main()

@@ -212,3 +212,58 @@ def test_two_ranks_shard_the_grid_and_reduce_like_one_process():
     assert res["times"] == [11.0]                                                        # MAX over ranks
     assert res["counts"] == [int(c["decisions"].sum()), int(c["ticks"].sum()), 6]        # SUM over ranks == single process
     assert np.array_equal(np.array(res["cum"]), log["cum_reward"][:, :3])                # env i gives the same curve on any rank
+
+
+# ---------------------------------------------------------------------------------------------- driver scripts (main.py / hyperparam_tuning.py)
+def _write_ini(path, out_dir, fixture=None, **model):
+    import configparser
+    c = configparser.ConfigParser()
+    c["MISC"] = {"random_seed": 450565, "out_dir": out_dir, "checkpoint_freq": 2, "exploit_freq": 2, "n_envs": 2}
+    c["ENV"] = {"width": 18, "height": 18, "max_num_cities": 5, "max_rails_between_cities": 1, "max_rail_pairs_in_city": 1,
+                "number_of_agents": 2, "malfunction_rate": 0.01, "min_duration": 5, "max_duration": 15}
+    if fixture:
+        c["ENV"]["fixture"] = fixture
+    c["MODEL"] = {"gamma": 1.0, "epsilon": 0.5, "epsilon_decay_rate": 0.9997, "lr": 0.1, "lr_decay_rate": 1.0, "default_q": 0.0,
+                  "num_episodes": 4, **model}
+    with open(path, "w") as f:
+        c.write(f)
+
+
+def test_cli_runs_the_reference_ini(capsys):
+    """main.py:13-78 with the reference's config.ini schema (hyperparam_tuning.py:51-78)."""
+    from switchfl_b200 import cli
+    emul = build_emul()
+    with tempfile.TemporaryDirectory() as tmp:
+        ini = os.path.join(tmp, "config.ini")
+        _write_ini(ini, os.path.join(tmp, "out"), fixture=os.path.join(ROOT, "tests", "golden", "c1_synth18.fixture.npz"))
+        model = cli.launch_experiment(ini, _engine_kwargs={"_emul_lib": emul})
+        out = capsys.readouterr().out
+        for line in ("DONE!", "TOTAL TIME:", "Seconds per episode:", "Flatland step time:", "Total step time:", "Total last time:",
+                     "Action selection time:", "Update time:", "Flatland reset time:", "Total reset time:"):          # main.py:68-78
+            assert line in out
+        assert os.path.exists(os.path.join(tmp, "out", "distr_q_model.pkl")) and os.path.exists(os.path.join(tmp, "out", "checkpoint_2.pkl"))
+        assert model.metrics["cum_reward"].shape == (2, 4)
+        # without ENV.fixture the synthetic generator builds a map of the requested size / train count
+        _write_ini(ini, os.path.join(tmp, "out2"))
+        m2 = cli.launch_experiment(ini, _engine_kwargs={"_emul_lib": emul})
+        assert m2.env.rail_env.width == 18 and m2.env.rail_env.get_num_agents() == 2
+
+
+def test_grid_launcher_writes_the_reference_tree():
+    """hyperparam_tuning.py:42-91: exp_i/seed_j/config.ini + outputs; grid points are the env axis of one engine."""
+    import configparser
+    from switchfl_b200 import cli
+    emul = build_emul()
+    env_section = {"width": 18, "height": 18, "max_num_cities": 5, "max_rails_between_cities": 1, "max_rail_pairs_in_city": 1,
+                   "number_of_agents": 2, "malfunction_rate": 0.0, "min_duration": 0, "max_duration": 0}
+    with tempfile.TemporaryDirectory() as tmp:
+        dirs = cli.launch_grid({"epsilon": [0.5, 0.1], "epsilon_decay_rate": [0.9997], "lr": [0.1], "lr_decay_rate": [1.0]},
+                               random_seeds=[64, 65], out_dir=tmp, env_section=env_section, num_episodes=3, checkpoint_freq=10 ** 9,
+                               exploit_freq=None, _engine_kwargs={"_emul_lib": emul})
+        assert sorted(os.path.relpath(d, tmp) for d in dirs) == ["exp_0/seed_0", "exp_0/seed_1", "exp_1/seed_0", "exp_1/seed_1"]
+        for d in dirs:
+            c = configparser.ConfigParser()
+            c.read(os.path.join(d, "config.ini"))
+            assert set(c["MODEL"]) == {"gamma", "epsilon", "epsilon_decay_rate", "lr", "lr_decay_rate", "default_q", "num_episodes"}
+            assert np.load(os.path.join(d, "cum_reward.npz"))["x"].shape == (3,)
+            assert isinstance(pickle.load(open(os.path.join(d, "distr_q_model.pkl"), "rb")), dict)
