@@ -333,7 +333,7 @@ def run_ours(args):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        tj = json.load(open(tpath))
+        tj = json.load(open(tpath)).get(args.workload, {})
         if tj.get("ticks") == args.ticks and tj.get("envs") == B:
             traffic = tj.get("dram_bytes_per_launch")
     line = {"metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

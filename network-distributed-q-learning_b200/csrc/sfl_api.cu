@@ -49,6 +49,9 @@ static int d2h(void *h, const void *d, size_t n, void *) { memcpy(h, d, n); retu
 static int dev_zero(void *d, size_t n, void *) { memset(d, 0, n); return 0; }
 #endif
 
+#ifndef SFL_MINB_BIG
+#define SFL_MINB_BIG 7                                 // CTAs per SM the large-map (tail in HBM) kernels are compiled for
+#endif
 #define SFL_WARPS_PER_CTA 4
 #define SFL_CTA_THREADS (32 * SFL_WARPS_PER_CTA)
 #define SFL_SMEM_BUDGET (56u * 1024u)                  // per CTA, so that four CTAs share an SM
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(SFL_CTA_THREADS) k_init(InitArgs ia) {
 // lists and -- when they fit -- semaphores, rewards and per-switch counters) is staged once per launch and written
 // back at the end, so the tick / decision loops touch HBM only for Q rows.
 template <int G, bool TRACE, bool TH>
-__global__ void __launch_bounds__(SFL_CTA_THREADS, (G == 32 || !TH) ? 7 : 4) k_run() {
+__global__ void __launch_bounds__(SFL_CTA_THREADS, TH ? (G == 32 ? 7 : 4) : SFL_MINB_BIG) k_run() {
   const int slot = threadIdx.x / G;                    // environment slot inside the CTA
   const int env_id = blockIdx.x * (blockDim.x / G) + slot;
   env_run<G, TRACE, TH>(env_id, (unsigned)slot * c_ra.env_smem, nullptr);
