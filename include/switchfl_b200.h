@@ -40,14 +40,17 @@ enum {
   SFL_ERR_PEND_FULL = 8,            /* pending-update list of a train full (distr_q.py:340-342)      */
   SFL_ERR_PLAN_FULL = 16,           /* train_action_plan longer than 4                               */
   SFL_ERR_REPLAY_UNDERRUN = 32,     /* replay action stream exhausted                                */
-  SFL_ERR_BAD_ACTION = 64           /* switch_env.py:213-215 assertion                               */
+  SFL_ERR_BAD_ACTION = 64,          /* switch_env.py:213-215 assertion                               */
+  SFL_ERR_REPLAY_DIVERGED = 128     /* replay: an action recorded as greedy is not the argmax here   */
 };
 
 /* run modes (sfl_run) */
 enum {
   SFL_MODE_LEARN = 0,    /* distr_q.py:296-366  epsilon-greedy + Q-update (Philox instead of PCG64)  */
   SFL_MODE_GREEDY = 1,   /* distr_q.py:195-224  test(): max_action only, no update                   */
-  SFL_MODE_REPLAY = 2,   /* learn() with the actions (and malfunction events) of a recorded trace    */
+  SFL_MODE_REPLAY = 2,   /* learn() with the actions (and malfunction events) of a recorded trace; an action
+                            with bit 6 set was an exploit choice: the row is looked up (inserted) and the
+                            recorded action must equal the argmax                                     */
   SFL_MODE_STEP = 3      /* host-driven AEC protocol (switch_env.py:616-666): one launch applies the action the
                             host chose for the waiting decision (replay_act[env * act_cap]), advances the trains to
                             the next decision point and reports it in step_out; no learning on the device            */

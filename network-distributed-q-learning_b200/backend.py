@@ -25,7 +25,8 @@ MODE_LEARN, MODE_GREEDY, MODE_REPLAY, MODE_STEP = 0, 1, 2, 3
 ERR_NO_TRAIN_AT_SWITCH = 1
 ERR_BITS = {1: "no train at active switch (observer.py:294-307)", 2: "infinite distance to target (observer.py:35-36)",
             4: "per-env Q table full (raise q_cap)", 8: "pending-update list full (raise pend_cap)",
-            16: "train action plan overflow", 32: "replay action stream exhausted", 64: "invalid action (switch_env.py:213-215)"}
+            16: "train action plan overflow", 32: "replay action stream exhausted", 64: "invalid action (switch_env.py:213-215)",
+            128: "replay diverged: an action recorded as greedy is not the argmax of the Q row"}
 
 _i32p, _u16p, _i8p, _u8p = C.POINTER(C.c_int32), C.POINTER(C.c_uint16), C.POINTER(C.c_int8), C.POINTER(C.c_uint8)
 

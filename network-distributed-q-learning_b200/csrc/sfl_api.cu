@@ -424,8 +424,8 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   ra.ep_delay = c->cfg.ep_cap > 0 ? (int *)c->bufs.ep_delay : nullptr;
   ra.replay_act = (const int8_t *)c->bufs.replay_act;
   ra.step_out = (sfl_step_rec *)c->bufs.step_out;
-  // recorded malfunction events replace the Philox draws in replay mode, and in step mode when a schedule was bound
-  ra.replay_ev = ((mode == SFL_MODE_REPLAY || mode == SFL_MODE_STEP) && c->cfg.ev_cap > 0) ? (const int *)c->bufs.replay_ev : nullptr;
+  // recorded malfunction events replace the Philox draws in replay mode, and in greedy / step mode when a schedule was bound (ev_cap > 0)
+  ra.replay_ev = (mode != SFL_MODE_LEARN && c->cfg.ev_cap > 0) ? (const int *)c->bufs.replay_ev : nullptr;
   const int trace = ra.trace_dec || ra.trace_tick || mode == SFL_MODE_STEP;      // the step protocol lives in the trace kernels
 #ifndef SFL_HOST_EMUL
   const int G = c->lanes;

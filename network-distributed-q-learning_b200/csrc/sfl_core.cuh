@@ -504,9 +504,19 @@ SFL_FN void decide(Env e, const sfl_hparams *hp, int env_id, int t) {
   int action = -1;
   if (c_ra.mode == SFL_MODE_REPLAY || c_ra.mode == SFL_MODE_STEP) {
     if (c_ra.mode == SFL_MODE_STEP) h->act_cursor = 0;         // the host's action for this decision
+    int exploited = 0;
     if (h->act_cursor >= c_ra.act_cap) { h->err |= SFL_ERR_REPLAY_UNDERRUN; action = A - 1; }
-    else action = c_ra.replay_act[(size_t)env_id * c_ra.act_cap + h->act_cursor++];
+    else {
+      action = c_ra.replay_act[(size_t)env_id * c_ra.act_cap + h->act_cursor++];
+      // bit 6 of a recorded action: the learner exploited, i.e. max_action was consulted -- which inserts the row
+      // (distr_q.py:318-319, 482); the replay then also checks that the recorded action IS the argmax
+      if (c_ra.mode == SFL_MODE_REPLAY && action >= 0 && (action & 0x40)) { exploited = 1; action &= 0x3F; }
+    }
     if (action < 0 || action >= A) { h->err |= SFL_ERR_BAD_ACTION; action = A - 1; }
+    if (exploited) {
+      my_row = q_row(e, hp, key);
+      if (max_action(my_row, A, mask) != action) h->err |= SFL_ERR_REPLAY_DIVERGED;
+    }
   } else if (c_ra.mode == SFL_MODE_LEARN) {
     double eps = dmul(hp->epsilon, e.sws()[s].eps_pow);
     U4 u = philox4x32((unsigned)h->step_counter, (unsigned)(hp->episode_base + h->episode), 0x5F1u, 0u, (unsigned)hp->seed, (unsigned)(hp->seed >> 32));
@@ -580,8 +590,11 @@ SFL_FN void decide(Env e, const sfl_hparams *hp, int env_id, int t) {
     }
     if (hit >= 0) {
       int2 pe = pend[hit];
-      if (!my_row) my_row = q_row(e, hp, key);                                    // max_q creates the row (distr_q.py:463-465)
-      q_update(e, hp, (unsigned)pe.x, (pe.y >> 24) & 15, (double)reward_in, my_row, (pe.y >> 12) & 0xFFF, s);
+      const int prev_sw = (pe.y >> 12) & 0xFFF;
+      // max_q creates the successor row (distr_q.py:463-465) -- but only when it is consulted: not for a train that
+      // stayed at the same switch (:444-447)
+      if (prev_sw != s && !my_row) my_row = q_row(e, hp, key);
+      q_update(e, hp, (unsigned)pe.x, (pe.y >> 24) & 15, (double)reward_in, my_row, prev_sw, s);
       SFL_NU
       for (int j = hit; j + 1 < n; j++) pend[j] = pend[j + 1];
       n--;

@@ -140,12 +140,18 @@ def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, verbose=True):
     T = rail_env.get_num_agents()
     NP = tab.NP
     dec = {k: [] for k in ("ep", "tick", "switch", "train", "obs", "mask", "reward", "action", "next_switch",
-                           "arrived", "sem", "done")}
+                           "arrived", "sem", "done", "greedy")}
     tick = {k: [] for k in ("ep", "tick", "pos", "dir", "state", "malf")}
     malf = []
     state = {"ep": -1, "qinit": None}
 
     orig_reset, orig_last, orig_step = env.reset, env.last, env.step
+    orig_max_action = model.max_action
+
+    def traced_max_action(*a, **k):          # distr_q.py:318-319: the exploit branch (it also inserts the row, :482)
+        pending["greedy"] = 1
+        return orig_max_action(*a, **k)
+    model.max_action = traced_max_action
     sw_index = {name2switch_id(n): i for i, n in enumerate(names)}
 
     def traced_reset(seed=None, options=None):
@@ -178,7 +184,7 @@ def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, verbose=True):
         obs, rew, term, trunc, info = r
         pending.update(obs=np.array(obs), reward=float(rew[env.active_train]), mask=np.array(info["action_mask"]),
                        switch=sw_index[name2switch_id(env.agent_selection)], train=int(env.active_train),
-                       tick=rail_env._elapsed_steps, done=bool(term or trunc))
+                       tick=rail_env._elapsed_steps, done=bool(term or trunc), greedy=0)
         if term or trunc:   # learn() breaks without stepping
             pass
         return r
@@ -190,7 +196,7 @@ def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, verbose=True):
         m = np.full(9, -1, np.int8); m[:len(pending["mask"])] = pending["mask"]
         dec["ep"].append(state["ep"]); dec["tick"].append(pending["tick"]); dec["switch"].append(pending["switch"])
         dec["train"].append(pending["train"]); dec["obs"].append(o); dec["mask"].append(m)
-        dec["reward"].append(pending["reward"]); dec["action"].append(int(action))
+        dec["reward"].append(pending["reward"]); dec["action"].append(int(action)); dec["greedy"].append(pending["greedy"])
         dec["next_switch"].append(sw_index[tuple(post["next_switch"])])
         dec["arrived"].append(sum(1 << int(h) for h in post["arrived_trains"]))
         dec["done"].append(int(env.terminated) | (int(env.truncated) << 1))
@@ -229,7 +235,7 @@ def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, verbose=True):
             keys[i, :len(k)] = np.array(k, np.int64); vals[i, :len(v)] = v
         return keys, vals
 
-    for k in ("ep", "tick", "switch", "train", "action", "next_switch", "done"):
+    for k in ("ep", "tick", "switch", "train", "action", "next_switch", "done", "greedy"):
         out["dec_" + k] = np.array(dec[k], np.int32)
     out["dec_arrived"] = np.array(dec["arrived"], np.uint64)
     out["dec_obs"] = np.array(dec["obs"], np.int64).reshape(-1, 18)

@@ -83,6 +83,13 @@ class SwitchFLOracle:
         self.trace = None
 
     # ------------------------------------------------------------------ env: reset (switch_env.py:93-158)
+    def replay_stream(self, first: int = 0, last: Optional[int] = None) -> np.ndarray:
+        """The recorded decisions as the engine's replay input: action | 0x40 where the learner exploited (max_action
+        was consulted, which also inserts the row: distr_q.py:318-319, 482)."""
+        a = np.array(self.trace["dec_action"][first:last], np.int8)
+        g = np.array(self.trace["dec_greedy"][first:last], np.int8)
+        return (a | (g << 6)).astype(np.int8)
+
     def malfunction_schedule(self) -> np.ndarray:
         """Every applied malfunction event (tick, train, duration) seen so far.  rail_env.reset(random_seed=seed)
         re-seeds flatland's RNG at every episode (switch_env.py:99), so the schedule repeats per episode and the
@@ -531,10 +538,16 @@ class SwitchFLOracle:
             obs, mask, _ = self.observe(s, h)
             reward = self.cumulative_rewards[s][h]
             tick = self.rail_env._elapsed_steps
+            was_greedy = 0
             if replay_actions is not None:
                 action = int(replay_actions[self.total_decisions])
+                if action & 0x40:                                                  # recorded as an exploit choice
+                    action &= 0x3F
+                    was_greedy = 1
+                    assert self.max_action(obs, s, mask) == action, "replayed greedy action differs from argmax"
             elif greedy:
                 action = self.max_action(obs, s, mask)
+                was_greedy = 1
             else:
                 eps = self.initial_epsilon * (self.epsilon_decay_rate ** self.agent_num_interactions[s])
                 if rng.random() < eps:                                             # distr_q.py:315-317
@@ -544,9 +557,11 @@ class SwitchFLOracle:
                     action = int(g.choice(valid)) if len(valid) else 0
                 else:
                     action = self.max_action(obs, s, mask)
+                    was_greedy = 1
             next_switch, arrived = self.env_step(s, h, action)
             if self.trace is not None:
                 self._trace_decision(tick, s, h, obs, mask, reward, action, next_switch, arrived)
+                self.trace["dec_greedy"].append(was_greedy)
             if learn:
                 if (s, h) in update_dict:                                          # distr_q.py:329-338
                     pobs, pact, pagent = update_dict.pop((s, h))
@@ -585,7 +600,7 @@ class SwitchFLOracle:
     # ------------------------------------------------------------------ tracing (same layout as tests/golden)
     def enable_trace(self):
         self.trace = {k: [] for k in ("dec_ep", "dec_tick", "dec_switch", "dec_train", "dec_obs", "dec_mask", "dec_reward",
-                                      "dec_action", "dec_next_switch", "dec_arrived", "dec_sem", "dec_done",
+                                      "dec_action", "dec_next_switch", "dec_arrived", "dec_sem", "dec_done", "dec_greedy",
                                       "tick_ep", "tick_tick", "tick_pos", "tick_dir", "tick_state", "tick_malf")}
 
     def _trace_tick(self):

@@ -22,6 +22,11 @@ def golden_events(g):
     return np.unique(ev[:, 1:], axis=0) if len(ev) else np.zeros((0, 3), np.int32)
 
 
+def replay_stream(g):
+    """recorded actions, bit 6 set where the reference learner exploited (max_action consulted)"""
+    return (g["dec_action"].astype(np.int8) | (g["dec_greedy"].astype(np.int8) << 6)).astype(np.int8)
+
+
 def make_replay_engine(name, factory, n_envs=2):
     fx, g = load_golden(name)
     rm = backend.RailMap(fx)
@@ -31,7 +36,7 @@ def make_replay_engine(name, factory, n_envs=2):
     eng = factory(rm, n_envs=n_envs, q_cap=q_cap, dec_cap=n_dec + 4, tick_cap=n_tick + 4, ep_cap=n_ep + 1,
                   act_cap=n_dec + 4, ev_cap=len(ev) + 2, trace_sem=True)
     eng.set_hparams(**hparams(g), seeds=np.arange(n_envs) + int(g["seed"]), episodes=n_ep)
-    eng.set_replay([g["dec_action"]] * n_envs, [ev] * n_envs)
+    eng.set_replay([replay_stream(g)] * n_envs, [ev] * n_envs)
     eng.reset()
     eng.enable_q_init(True)
     return fx, g, rm, eng
@@ -101,3 +106,59 @@ def check_replay(name, factory, n_envs=2, chunk=None):
                 assert np.allclose(q[k], row, rtol=1e-12, atol=0.0), (k, q[k], row)
     eng.close()
     return True
+
+
+def check_against_oracle(factory, fx, hp, n_ep, seeds, max_steps=100_000, greedy_after=False, q_cap=4096):
+    """The oracle free-runs learn() (and optionally one greedy test() rollout) per seed; the engine replays each
+    env's action / malfunction stream and must agree on every decision, the episode metrics and the Q-table --
+    including episodes cut short by max_steps (switch_env.py:652-657) and the rows test() inserts (distr_q.py:211)."""
+    from oracle.switchfl_oracle import SwitchFLOracle
+    rm = backend.RailMap(fx)
+    B = len(seeds)
+    oracles, acts, evs, n_learn = [], [], [], []
+    for sd in seeds:
+        o = SwitchFLOracle(fx, rm.tab, seed=int(sd), max_steps=max_steps, **hp)
+        o.enable_trace()
+        eps = o.learn(n_ep)
+        n_learn.append(len(o.trace["dec_action"]))
+        if greedy_after:
+            o.episode = n_ep
+            eps.append(o.test())
+        o.eps = eps
+        oracles.append(o)
+        acts.append(o.replay_stream(0, n_learn[-1]))
+        evs.append(o.malfunction_schedule())
+    n_dec = max(len(o.trace["dec_action"]) for o in oracles)
+    eng = factory(rm, n_envs=B, q_cap=q_cap, max_steps=max_steps, dec_cap=n_dec + 4, act_cap=n_dec + 4,
+                  ev_cap=max(len(e) for e in evs) + 2, ep_cap=n_ep + 2)
+    eng.set_hparams(**hp, seeds=np.asarray(seeds), episodes=n_ep)
+    eng.set_replay(acts, evs)
+    eng.reset()
+    eng.enable_q_init(True)
+    eng.run(backend.MODE_REPLAY, 1_000_000)
+    eng.check_errors()
+    assert (eng.counters()["halted"] == 1).all()
+    if greedy_after:
+        eng.set_hparams(**hp, seeds=np.asarray(seeds), episodes=1, episode_base=n_ep)
+        eng.reset(keep_q=True, keep_interactions=True)
+        eng.run(backend.MODE_GREEDY, 1_000_000)
+        eng.check_errors()
+    _, log, delays = eng.episode_log()
+    for i, o in enumerate(oracles):
+        dec, _, _ = eng.trace(i)
+        t = o.trace
+        first = n_learn[i] if greedy_after else 0                      # the trace buffers restart with sfl_reset
+        assert len(dec) == len(t["dec_action"]) - first, (i, len(dec), len(t["dec_action"]), first)
+        for k_mine, k_o in (("sw", "dec_switch"), ("train", "dec_train"), ("action", "dec_action"), ("next_sw", "dec_next_switch"),
+                            ("tick", "dec_tick"), ("done", "dec_done")):
+            assert np.array_equal(dec[k_mine], np.array(t[k_o][first:])), (i, k_mine)
+        assert np.array_equal(dec["reward"].astype(np.float64), np.array(t["dec_reward"][first:])), i
+        eps = o.eps[n_ep:] if greedy_after else o.eps
+        for e_i, ep in enumerate(eps):
+            assert log[i, e_i]["cum_reward"] == ep["cum_reward"] and log[i, e_i]["decisions"] == ep["decisions"], (i, e_i)
+            assert log[i, e_i]["arrived"] == ep["arrived"] and log[i, e_i]["ticks"] == ep["ticks"], (i, e_i)
+            assert log[i, e_i]["num_malfunctions"] == ep["num_malfunctions"], (i, e_i)
+            assert list(delays[i, e_i]) == [int(x) for x in ep["delays"]], (i, e_i)
+        q = eng.export_q(i, include_init=True)
+        assert q == o.q_table, (i, len(q), len(o.q_table))
+    eng.close()

@@ -169,3 +169,39 @@ def check_aec(env, g):
             assert touched[k] == v, (k, touched[k], v)
         else:
             assert np.allclose(touched[k], v, rtol=1e-12, atol=0), (k, touched[k], v)
+
+
+# ---------------------------------------------------------------------------------------------- edge cases vs the free-running oracle
+HP_EDGE = dict(gamma=0.9, epsilon=0.6, epsilon_decay_rate=0.999, lr=0.2, lr_decay_rate=1.0, default_q=0.5)
+
+
+def edge_fixture(kind):
+    from switchfl_b200 import mapgen
+    if kind == "one_train":
+        return mapgen.make_fixture(18, 1, 4, seed=3, num_cities=2, malfunction_rate=0.05, min_duration=2, max_duration=4)
+    if kind == "max_trains":                                   # SFL_MAX_T = 64: both words of every train bit-set
+        return mapgen.make_fixture(64, 64, 40, seed=3, num_cities=8, malfunction_rate=0.02, min_duration=3, max_duration=9, p_slip=0.4)
+    raise KeyError(kind)
+
+
+def test_emul_truncation_by_max_steps(emul_lib):
+    """switch_env.py:652-657: the episode is truncated once more than max_steps decisions were taken."""
+    from tests._parity import check_against_oracle
+    from tests._util import load_golden
+    fx, _ = load_golden("slips24_t6")
+    check_against_oracle(lambda rm, **kw: backend.Engine(rm, _emul_lib=emul_lib, **kw), fx, HP_EDGE, 3, [5, 6], max_steps=25)
+
+
+def test_emul_greedy_rollout_after_training(emul_lib):
+    """distr_q.py:184-241 test(): greedy rollout, no updates, but default rows are inserted on lookup."""
+    from tests._parity import check_against_oracle
+    from tests._util import load_golden
+    fx, _ = load_golden("slips24_t6")
+    check_against_oracle(lambda rm, **kw: backend.Engine(rm, _emul_lib=emul_lib, **kw), fx, HP_EDGE, 2, [11, 12], greedy_after=True)
+
+
+@pytest.mark.parametrize("kind", ["one_train", "max_trains"])
+def test_emul_train_count_extremes(kind, emul_lib):
+    from tests._parity import check_against_oracle
+    check_against_oracle(lambda rm, **kw: backend.Engine(rm, _emul_lib=emul_lib, **kw), edge_fixture(kind), HP_EDGE, 1, [21, 22],
+                         q_cap=65536 if kind == "max_trains" else 1024)

@@ -42,7 +42,7 @@ def test_cuda_replay_many_seeds_against_oracle():
         o.enable_trace()
         o.learn(n_ep)
         oracles.append(o)
-        acts.append(np.array(o.trace["dec_action"], np.int8))
+        acts.append(o.replay_stream())
         evs.append(o.malfunction_schedule())
     n_dec = max(len(a) for a in acts)
     eng = gpu_engine(rm, n_envs=B, q_cap=1024, dec_cap=n_dec + 4, act_cap=n_dec + 4, ev_cap=max(len(e) for e in evs) + 2, ep_cap=n_ep + 1)
@@ -159,3 +159,54 @@ def test_cuda_step_batch_lockstep_equals_single_env():
         assert k == len(logs[i])
         one.engine.close()
     env.engine.close()
+
+
+# ---------------------------------------------------------------------------------------------- edge cases vs the free-running oracle
+def test_cuda_truncation_by_max_steps():
+    from tests._parity import check_against_oracle
+    from tests.test_emul_parity import HP_EDGE
+    fx, _ = load_golden("slips24_t6")
+    check_against_oracle(gpu_engine, fx, HP_EDGE, 3, [5, 6, 7], max_steps=25)
+
+
+def test_cuda_greedy_rollout_after_training():
+    from tests._parity import check_against_oracle
+    from tests.test_emul_parity import HP_EDGE
+    fx, _ = load_golden("slips24_t6")
+    check_against_oracle(gpu_engine, fx, HP_EDGE, 2, [11, 12, 13], greedy_after=True)
+
+
+@pytest.mark.parametrize("kind", ["one_train", "max_trains"])
+def test_cuda_train_count_extremes(kind):
+    from tests._parity import check_against_oracle
+    from tests.test_emul_parity import HP_EDGE, edge_fixture
+    check_against_oracle(gpu_engine, edge_fixture(kind), HP_EDGE, 1, [21, 22, 23], q_cap=65536 if kind == "max_trains" else 1024)
+
+
+def test_cuda_replay_detects_a_wrong_greedy_action():
+    """An action recorded as an exploit choice must be the argmax of the row on the device, else the env is flagged."""
+    from tests._parity import make_replay_engine, replay_stream
+    fx, g, rm, eng = make_replay_engine("c1_synth18", gpu_engine, n_envs=2)
+    stream = replay_stream(g).copy()
+    i = int(np.nonzero(g["dec_greedy"])[0][3])
+    allowed = [a for a in range(9) if a < len([x for x in g["dec_mask"][i] if x >= 0]) and g["dec_mask"][i][a] == 1 and a != g["dec_action"][i]]
+    if allowed:
+        stream[i] = np.int8(allowed[0] | 0x40)
+        eng.set_replay([replay_stream(g), stream], None)
+        eng.run(backend.MODE_REPLAY, 100000)
+        err = eng.counters()["err"]
+        assert err[0] == 0 and err[1] & 128
+    eng.close()
+
+
+def test_q_table_full_is_reported_loudly():
+    fx, _ = load_golden("slips24_t6")
+    rm = backend.RailMap(fx)
+    eng = gpu_engine(rm, n_envs=4, q_cap=8)
+    eng.set_hparams(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0, episodes=2)
+    eng.reset()
+    eng.enable_q_init(True)
+    eng.run(backend.MODE_LEARN, 100000)
+    with pytest.raises(RuntimeError, match="Q table full"):
+        eng.check_errors()
+    eng.close()

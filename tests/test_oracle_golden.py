@@ -16,7 +16,7 @@ def test_oracle_matches_reference_trace(name):
     o.enable_trace()
     eps = o.learn(int(g["n_episodes"]))
     t = o.trace
-    for k in ("dec_ep", "dec_tick", "dec_switch", "dec_train", "dec_action", "dec_next_switch", "dec_done"):
+    for k in ("dec_ep", "dec_tick", "dec_switch", "dec_train", "dec_action", "dec_next_switch", "dec_done", "dec_greedy"):
         assert np.array_equal(np.array(t[k], np.int32), g[k]), k
     assert np.array_equal(np.array(t["dec_obs"]).reshape(-1, 18), g["dec_obs"])
     assert np.array_equal(np.array(t["dec_mask"]).reshape(-1, 9), g["dec_mask"])
@@ -50,7 +50,7 @@ def test_oracle_replay_equals_free_run(name):
     sched = {(int(t), int(h)): int(d) for (_, t, h, d) in ev}
     o.rail_env.injected_malfunctions = sched
     o.enable_trace()
-    o.learn(int(g["n_episodes"]), replay_actions=g["dec_action"])
+    o.learn(int(g["n_episodes"]), replay_actions=g["dec_action"] | (g["dec_greedy"] << 6))
     assert np.array_equal(np.array(o.trace["tick_pos"], np.int32).reshape(g["tick_pos"].shape), g["tick_pos"])
     assert np.array_equal(np.array(o.trace["tick_malf"], np.int32).reshape(g["tick_malf"].shape), g["tick_malf"])
     assert np.array_equal(np.array(o.trace["dec_reward"]), g["dec_reward"])
