@@ -149,7 +149,10 @@ typedef struct sfl_step_rec {
 } sfl_step_rec;
 
 typedef struct sfl_tick_rec { int32_t pos; int8_t dir, state; int16_t malf; } sfl_tick_rec;
-typedef struct sfl_ep_rec { double cum_reward; int32_t decisions, arrived, num_malfunctions, ticks; } sfl_ep_rec;
+typedef struct sfl_ep_rec {            /* one finished episode (distr_q.py:360-366)                   */
+  double cum_reward; int32_t decisions, arrived, num_malfunctions, ticks;
+  uint64_t arrived_mask;               /* the trains at their destination ("arrived_trains", :345, 371) */
+} sfl_ep_rec;
 
 int sfl_abi_version(void);
 const char *sfl_last_error(void);

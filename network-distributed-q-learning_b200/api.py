@@ -301,6 +301,7 @@ class DistrQLearning:
                 cum_reward[:, done:done + seg] = log["cum_reward"][:, :seg]
                 arrived[:, done:done + seg] = log["arrived"][:, :seg]
                 num_malf[:, done:done + seg] = log["num_malfunctions"][:, :seg]
+                last_mask = log["arrived_mask"][:, seg - 1].copy()
                 delays[:, done:done + seg] = dl[:, :seg]
                 done += seg
             if cut >= num_episodes:
@@ -319,7 +320,8 @@ class DistrQLearning:
                 np.savez_compressed(os.path.join(out_dir, f"num_malfunctions_checkpoint_{cut + 1}.npz"), x=num_malf[p, :cut])
         self._table_dirty = True
         self.q_table = eng.export_q(p, include_init=self._q_inited, default_q=self._default_q_of(p))
-        self.metrics = dict(cum_reward=cum_reward, arrived_trains=arrived, delays=delays, num_malfunctions=num_malf,
+        at_dest = [[h for h in range(T) if (int(mk) >> h) & 1] for mk in last_mask] if num_episodes else [[] for _ in range(B)]
+        self.metrics = dict(cum_reward=cum_reward, arrived_trains=arrived, delays=delays, num_malfunctions=num_malf, trains_at_dest=at_dest,
                             cum_reward_exploit=np.array(cum_reward_exploit), arrived_trains_exploit=np.array(arrived_exploit),
                             wall_s=time.time() - t_start)
         if out_dir:
@@ -343,6 +345,7 @@ class DistrQLearning:
         np.savez_compressed(os.path.join(out_dir, "arrived_trains.npz"), x=m["arrived_trains"][i])
         np.savez_compressed(os.path.join(out_dir, "delays.npz"), x=m["delays"][i])
         np.savez_compressed(os.path.join(out_dir, "num_malfunctions.npz"), x=m["num_malfunctions"][i])
+        np.savez_compressed(os.path.join(out_dir, "trains_at_dest.npz"), x=m["trains_at_dest"][i])     # distr_q.py:371
         if exploit:
             np.savez_compressed(os.path.join(out_dir, "cum_reward_exploit.npz"), x=[r[i] for r in m["cum_reward_exploit"]])
             np.savez_compressed(os.path.join(out_dir, "arrived_trains_exploit.npz"), x=[a[i] for a in m["arrived_trains_exploit"]])

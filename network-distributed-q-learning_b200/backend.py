@@ -69,8 +69,8 @@ DEC_DT = np.dtype([("ep", "i4"), ("tick", "i4"), ("sw", "i4"), ("train", "i4"), 
 TICK_DT = np.dtype([("pos", "i4"), ("dir", "i1"), ("state", "i1"), ("malf", "i2")])
 STEP_DT = np.dtype([("pending", "i4"), ("sw", "i4"), ("train", "i4"), ("key", "u4"), ("mask", "i4"), ("done", "i4"), ("elapsed", "i4"),
                     ("last_next_sw", "i4"), ("arrived", "u8"), ("rewards", "i4", (64,))])
-EP_DT = np.dtype([("cum_reward", "f8"), ("decisions", "i4"), ("arrived", "i4"), ("num_malfunctions", "i4"), ("ticks", "i4")])
-assert HPARAMS_DT.itemsize == 80 and COUNTERS_DT.itemsize == 64 and DEC_DT.itemsize == 48 and TICK_DT.itemsize == 8 and EP_DT.itemsize == 24
+EP_DT = np.dtype([("cum_reward", "f8"), ("decisions", "i4"), ("arrived", "i4"), ("num_malfunctions", "i4"), ("ticks", "i4"), ("arrived_mask", "u8")])
+assert HPARAMS_DT.itemsize == 80 and COUNTERS_DT.itemsize == 64 and DEC_DT.itemsize == 48 and TICK_DT.itemsize == 8 and EP_DT.itemsize == 32
 
 
 def load_library(path: Optional[str] = None) -> C.CDLL:

@@ -943,7 +943,7 @@ SFL_FN void episode_end(Env e, int env_id) {   // first lane
   if (c_ra.ep_log && h->n_ep_logged < c_ra.ep_cap) {
     sfl_ep_rec *rec = c_ra.ep_log + (size_t)env_id * c_ra.ep_cap + h->n_ep_logged;
     rec->cum_reward = h->cum_reward; rec->decisions = h->step_counter; rec->arrived = popc64(h->done_mask);
-    rec->num_malfunctions = h->num_malf; rec->ticks = h->elapsed;
+    rec->num_malfunctions = h->num_malf; rec->ticks = h->elapsed; rec->arrived_mask = h->done_mask;
     if (c_ra.ep_delay) {
       int *d = c_ra.ep_delay + ((size_t)env_id * c_ra.ep_cap + h->n_ep_logged) * c_L.T;
       SFL_NU

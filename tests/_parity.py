@@ -116,18 +116,30 @@ def check_against_oracle(factory, fx, hp, n_ep, seeds, max_steps=100_000, greedy
     rm = backend.RailMap(fx)
     B = len(seeds)
     oracles, acts, evs, n_learn = [], [], [], []
+    kept = []
     for sd in seeds:
         o = SwitchFLOracle(fx, rm.tab, seed=int(sd), max_steps=max_steps, **hp)
         o.enable_trace()
-        eps = o.learn(n_ep)
-        n_learn.append(len(o.trace["dec_action"]))
-        if greedy_after:
-            o.episode = n_ep
-            eps.append(o.test())
+        try:
+            eps = o.learn(n_ep)
+            n_dec_learn = len(o.trace["dec_action"])
+            if greedy_after:
+                o.episode = n_ep
+                eps.append(o.test())
+        except RuntimeError as ex:                 # the reference dies here too (observer.py:294-307); covered by its own test
+            if "No train detected" not in str(ex):
+                raise
+            continue
+        kept.append(sd)
+        n_learn.append(n_dec_learn)
         o.eps = eps
         oracles.append(o)
         acts.append(o.replay_stream(0, n_learn[-1]))
         evs.append(o.malfunction_schedule())
+    seeds, B = kept, len(kept)
+    if not B:
+        import pytest
+        pytest.skip("the reference itself fails on this map for every seed (observer.py:294-307)")
     n_dec = max(len(o.trace["dec_action"]) for o in oracles)
     eng = factory(rm, n_envs=B, q_cap=q_cap, max_steps=max_steps, dec_cap=n_dec + 4, act_cap=n_dec + 4,
                   ev_cap=max(len(e) for e in evs) + 2, ep_cap=n_ep + 2)
@@ -156,7 +168,9 @@ def check_against_oracle(factory, fx, hp, n_ep, seeds, max_steps=100_000, greedy
         eps = o.eps[n_ep:] if greedy_after else o.eps
         for e_i, ep in enumerate(eps):
             assert log[i, e_i]["cum_reward"] == ep["cum_reward"] and log[i, e_i]["decisions"] == ep["decisions"], (i, e_i)
-            assert log[i, e_i]["arrived"] == ep["arrived"] and log[i, e_i]["ticks"] == ep["ticks"], (i, e_i)
+            assert log[i, e_i]["ticks"] == ep["ticks"], (i, e_i)
+            if ep["decisions"]:                    # with no decision at all the reference has no post_step_info to count (distr_q.py:364)
+                assert log[i, e_i]["arrived"] == ep["arrived"] == bin(int(log[i, e_i]["arrived_mask"])).count("1"), (i, e_i)
             assert log[i, e_i]["num_malfunctions"] == ep["num_malfunctions"], (i, e_i)
             assert list(delays[i, e_i]) == [int(x) for x in ep["delays"]], (i, e_i)
         q = eng.export_q(i, include_init=True)

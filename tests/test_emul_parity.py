@@ -205,3 +205,30 @@ def test_emul_train_count_extremes(kind, emul_lib):
     from tests._parity import check_against_oracle
     check_against_oracle(lambda rm, **kw: backend.Engine(rm, _emul_lib=emul_lib, **kw), edge_fixture(kind), HP_EDGE, 1, [21, 22],
                          q_cap=65536 if kind == "max_trains" else 1024)
+
+
+def fuzz_case(i):
+    """Deterministic pseudo-random (map, timetable, hyper-parameters) case i."""
+    import numpy as np
+    from switchfl_b200 import mapgen
+    r = np.random.RandomState(1000 + i)
+    n = int(r.choice([12, 16, 20, 28, 36]))
+    trains = int(r.randint(1, 10))
+    fx = mapgen.make_fixture(n, trains, int(r.randint(2, 3 + n // 2)), seed=int(r.randint(10 ** 6)), num_cities=int(r.randint(2, 6)),
+                             malfunction_rate=float(r.choice([0.0, 0.01, 0.08])), min_duration=int(r.randint(1, 4)),
+                             max_duration=int(r.randint(4, 12)), p_slip=float(r.choice([0.0, 0.3, 0.8])))
+    hp = dict(gamma=float(r.choice([1.0, 0.9, 0.5])), epsilon=float(r.choice([0.2, 0.5, 1.0])), epsilon_decay_rate=float(r.choice([1.0, 0.999, 0.9])),
+              lr=float(r.choice([0.1, 0.5, 1.0])), lr_decay_rate=1.0, default_q=float(r.choice([0.0, -3.5, 200.0])))
+    return fx, hp, [int(x) for x in r.randint(0, 10 ** 6, size=2)], int(r.choice([100_000, 100_000, 40]))
+
+
+@pytest.mark.parametrize("i", range(12))
+def test_emul_fuzz_maps_against_oracle(i, emul_lib):
+    """Random maps / timetables / hyper-parameters: oracle free run vs engine replay, incl. a greedy rollout."""
+    from tests._parity import check_against_oracle
+    try:
+        fx, hp, seeds, max_steps = fuzz_case(i)
+    except ValueError as ex:                                    # "map too small for the requested number of trains"
+        pytest.skip(str(ex))
+    check_against_oracle(lambda rm, **kw: backend.Engine(rm, _emul_lib=emul_lib, **kw), fx, hp, 3, seeds, max_steps=max_steps,
+                         greedy_after=True, q_cap=16384)

@@ -210,3 +210,50 @@ def test_q_table_full_is_reported_loudly():
     with pytest.raises(RuntimeError, match="Q table full"):
         eng.check_errors()
     eng.close()
+
+
+@pytest.mark.parametrize("i", [0, 3, 5, 7, 8, 11])
+def test_cuda_fuzz_maps_against_oracle(i):
+    """Random maps / timetables / hyper-parameters (the CPU suite runs the same cases on the host build)."""
+    from tests._parity import check_against_oracle
+    from tests.test_emul_parity import fuzz_case
+    try:
+        fx, hp, seeds, max_steps = fuzz_case(i)
+    except ValueError as ex:
+        pytest.skip(str(ex))
+    check_against_oracle(gpu_engine, fx, hp, 3, seeds, max_steps=max_steps, greedy_after=True, q_cap=16384)
+
+
+def test_cuda_learn_c4_size_properties():
+    """BASELINE config C4 size (100x100, 50 trains, 8192 envs per GPU): free-running learn; size-independent invariants.
+    On this congested map the reference itself can die in observer.py:294-307; those episodes are abandoned and counted."""
+    fx, _ = load_golden("c4_synth100_t50")
+    rm = backend.RailMap(fx)
+    B, n_ep = 8192, 2
+    eng = gpu_engine(rm, n_envs=B, q_cap=8192, ep_cap=4)
+    hp = dict(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0)
+    eng.set_hparams(**hp, seeds=np.arange(B) + 450565, episodes=n_ep)
+    eng.reset()
+    eng.enable_q_init(True)
+    eng.run(backend.MODE_LEARN, 100000)
+    eng.check_errors(allow=backend.ERR_NO_TRAIN_AT_SWITCH)
+    c = eng.counters()
+    assert (c["halted"] == 1).all() and (c["episodes"] == n_ep).all()
+    assert ((c["aborted"] > 0) == (c["err"] != 0)).all() and (c["aborted"] <= n_ep).all()
+    n, log, delays = eng.episode_log()
+    assert (n == n_ep).all()
+    assert (log["decisions"][:, :n_ep].sum(axis=1) == c["decisions"]).all()          # bookkeeping closes
+    assert (log["ticks"][:, :n_ep].sum(axis=1) == c["ticks"]).all()
+    assert (log["ticks"][:, :n_ep] <= int(fx["max_episode_steps"])).all()
+    full = (c["aborted"] == 0)
+    assert (log["ticks"][full][:, :n_ep] == int(fx["max_episode_steps"])).all() | (log["arrived"][full][:, :n_ep] == 50).all()
+    pop = np.array([[bin(int(m)).count("1") for m in row[:n_ep]] for row in log["arrived_mask"]])
+    assert (pop == log["arrived"][:, :n_ep]).all()
+    d, t = eng.total_decisions()
+    assert d == int(c["decisions"].sum()) and t == int(c["ticks"].sum())
+    first = c.copy()
+    eng.reset()                                                                     # same seeds -> the same trajectories
+    eng.run(backend.MODE_LEARN, 100000)
+    c2 = eng.counters()
+    assert np.array_equal(c2["decisions"], first["decisions"]) and np.array_equal(c2["aborted"], first["aborted"])
+    eng.close()

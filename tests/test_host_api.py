@@ -117,7 +117,7 @@ def test_drop_in_learn_outputs_have_the_reference_layout():
     with tempfile.TemporaryDirectory() as out:
         model.learn(num_episodes=6, out_dir=out, checkpoint_freq=3, exploit_freq=2)
         model.save(os.path.join(out, "distr_q_model.pkl"))
-        for name in ("cum_reward", "arrived_trains", "delays", "num_malfunctions", "cum_reward_exploit", "arrived_trains_exploit",
+        for name in ("cum_reward", "arrived_trains", "delays", "num_malfunctions", "trains_at_dest", "cum_reward_exploit", "arrived_trains_exploit",
                      "cum_reward_checkpoint_3", "arrived_trains_checkpoint_3", "delays_checkpoint_3", "trains_at_dest_checkpoint_3",
                      "num_malfunctions_checkpoint_3"):
             with np.load(os.path.join(out, name + ".npz")) as z:
