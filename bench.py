@@ -45,14 +45,20 @@ WORKLOADS = {
     "c4": ("c4_synth100_t50", 8192, 8192,
            "C4: large synthetic map (100x100, 50 trains, 281 switches, malfunctions), 65536 envs per 8 GPUs = 8192 per GPU, "
            "distributed Q-learning, learn mode"),
+    "c5": ("c4_synth100_t50", 8192, 2,
+           "C5 (extension, no reference counterpart): the C4 map in shared-table mode -- all 8192 envs of a GPU read one dense "
+           "Q table and accumulate TD steps; every step (512 ticks) the integer accumulators are all-reduced over the GPUs "
+           "(NCCL) and the mean step is folded into the table"),
 }
+SHARED_Q = False
 FIXTURE = os.path.join(ROOT, "tests", "golden", "c1_synth18.fixture.npz")
 WORKLOAD = WORKLOADS["c2"][3]
 
 
 def select_workload(args):
-    global FIXTURE, WORKLOAD
+    global FIXTURE, WORKLOAD, SHARED_Q
     name, envs, q_cap, desc = WORKLOADS[args.workload]
+    SHARED_Q = args.workload == "c5"
     FIXTURE = name if name.startswith("@") else os.path.join(ROOT, "tests", "golden", name + ".fixture.npz")
     WORKLOAD = desc if not args.envs or args.envs == envs else desc + f" [envs per GPU overridden: {args.envs}]"
     args.envs = args.envs or envs
@@ -233,16 +239,24 @@ def run_ours(args):
 
     # ---------------- device-resident arm: Engine level, CUDA-event timed (one engine per map, one stream)
     rms = [backend.RailMap(fx) for fx in fxs]
-    engs = [backend.Engine(rm, n_envs=Bp, device=dev, q_cap=args.q_cap, ep_cap=4, lanes=args.lanes or None) for rm in rms]
+    engs = [backend.Engine(rm, n_envs=Bp, device=dev, q_cap=args.q_cap, ep_cap=4, lanes=args.lanes or None, shared_q=SHARED_Q) for rm in rms]
     lanes = engs[0].lanes
     for k, eng in enumerate(engs):
         eng.set_hparams(**HP, seeds=seeds_of(k), episodes=-1)
         eng.reset()
         eng.enable_q_init(True)
+        if SHARED_Q:
+            eng.init_shared_q(HP["default_q"])
+
+    def launch(eng):
+        eng.run(backend.MODE_LEARN, args.ticks)
+        if SHARED_Q:
+            eng.shared_q_sync(dist)                                       # all-reduce of the accumulators + apply kernel
+
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         for eng in engs:
-            eng.run(backend.MODE_LEARN, args.ticks)
+            launch(eng)
     barrier()
 
     def totals():
@@ -261,7 +275,7 @@ def run_ours(args):
     for a, b in evs:
         a.record()
         for eng in engs:
-            eng.run(backend.MODE_LEARN, args.ticks)
+            launch(eng)
         b.record()
     stop.record()
     barrier()
@@ -289,8 +303,8 @@ def run_ours(args):
     models = []
     for k, fx in enumerate(fxs):
         env = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=Bp, device=dev, q_cap=args.q_cap, ep_cap=4,
-                                 _engine_kwargs={"lanes": args.lanes or None})
-        models.append(api.DistrQLearning(env=env, seeds=seeds_of(k), **HP))
+                                 shared_q=SHARED_Q, _engine_kwargs={"lanes": args.lanes or None})
+        models.append(api.DistrQLearning(env=env, seeds=seeds_of(k), dist=dist, **HP))
     for _ in range(args.warmup):
         for m in models:
             m.learn_chunk(args.ticks)
@@ -343,12 +357,13 @@ def run_ours(args):
                        "train_ticks_per_decision": k_bar, "ticks": ticks, "episodes_rank0": episodes,
                        "episodes_abandoned_rank0": aborted, "q_rows_max_rank0": q_rows_max,
                        "l2": f"inputs larger than L2: {state_mb:.0f} MB of env state + Q tables per GPU vs 126 MB L2",
-                       "sharding": "envs by seed range, no data-path collective"},
+                       "sharding": ("envs by seed range; per step one integer all-reduce (sum) of the shared table's accumulators" if SHARED_Q
+                                    else "envs by seed range, no data-path collective")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_run", "bytes_per_decision": bpd, "kernel_ms": kern_ms, "peak_source": peak_src,
                          "note": "per-env decision chains are serial: latency/issue-bound, not HBM-bound (SURVEY 8d honest note)"},
             "e2e": {"value": e2e_dec / e2e_s, "unit": "decisions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps * parts, "clocks": clocks}
+            "gpu_launches": args.steps * parts * (2 if SHARED_Q else 1), "clocks": clocks}
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         d, busy, wall, eps = cpu_sample(args.cpu_seconds, cores)

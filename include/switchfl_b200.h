@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SFL_ABI_VERSION 3
+#define SFL_ABI_VERSION 4
 
 enum {
   SFL_OK = 0,
@@ -85,6 +85,9 @@ typedef struct sfl_config {
   int32_t ep_cap;               /* episode-log capacity per env                                       */
   int32_t act_cap, ev_cap;      /* replay capacities per env                                          */
   int32_t trace_sem;            /* 1: also log the semaphore table after each decision                */
+  int32_t shared_q;             /* 1: shared-table mode (extension, no counterpart in the reference): every environment
+                                   of this context reads ONE dense Q table and accumulates its TD steps into a delta
+                                   buffer; sfl_shared_q_apply folds the mean step into the table  */
 } sfl_config;
 
 /* DistrQLearning.__init__ arguments (distr_q.py:32) + MalfunctionParameters (main.py:28-33), per env */
@@ -108,6 +111,9 @@ typedef struct sfl_sizes {
   uint64_t replay_act_bytes, replay_ev_bytes;
   uint64_t counters_bytes;      /* n_envs * sizeof(sfl_env_counters)                                  */
   uint64_t step_out_bytes;      /* n_envs * sizeof(sfl_step_rec) (SFL_MODE_STEP only)                 */
+  uint64_t shared_q_bytes;      /* shared-table mode: NP*NT*48 rows x a_max doubles (the table)       */
+  uint64_t shared_d_bytes;      /*   ... x a_max int64 (sum of TD steps, fixed point 2^-24)           */
+  uint64_t shared_c_bytes;      /*   ... x a_max int32 (number of TD steps)                           */
   int32_t q_stride;             /* doubles per Q row (1 key slot + A_max)                             */
   int32_t a_max;
 } sfl_sizes;
@@ -118,6 +124,7 @@ typedef struct sfl_buffers {    /* all device pointers; optional ones may be NUL
   void *ep_log; void *ep_delay;
   void *replay_act; void *replay_ev;
   void *step_out;
+  void *shared_q; void *shared_d; void *shared_c;    /* shared-table mode; shared_d / shared_c may be all-reduced (sum) by the caller */
 } sfl_buffers;
 
 typedef struct sfl_env_counters {      /* written by sfl_run for every env                            */
@@ -181,6 +188,11 @@ int sfl_enable_q_init(void *ctx, int on);
 /* advance every env by up to max_ticks flatland ticks (all decisions in between included);
  * replaces the loop body of DistrQLearning.learn / test  (distr_q.py:302-362, 199-224)               */
 int sfl_run(void *ctx, int mode, int max_ticks, void *stream);
+
+/* Shared-table mode: Q[s][a] += (sum of the TD steps proposed for (s, a) since the last apply) / (their number), then
+ * the delta buffers are cleared.  Across GPUs the caller all-reduces shared_d and shared_c (integer sums: order
+ * independent, bit-reproducible) before calling this, which leaves identical tables on every rank.                 */
+int sfl_shared_q_apply(void *ctx, void *stream);
 
 /* sum of decisions over all envs after the last run (device reduction, 8-byte D2H)                   */
 int sfl_total_decisions(void *ctx, uint64_t *decisions, uint64_t *ticks, void *stream);

@@ -83,7 +83,8 @@ class ASyncSwitchEnv:
     per-decision protocol (agent_iter / last / step) is executed on the device by the learner's kernel."""
 
     def __init__(self, rail_env: RailEnv, max_steps: int = 200, render_mode=None, observer=None, seed=None,
-                 n_envs: int = 1, device: str = "cuda:0", q_cap: int = 1024, ep_cap: int = 128, _engine_kwargs=None):
+                 n_envs: int = 1, device: str = "cuda:0", q_cap: int = 1024, ep_cap: int = 128, shared_q: bool = False,
+                 _engine_kwargs=None):
         self.rail_env = rail_env
         self.max_steps = max_steps
         self.render_mode = render_mode
@@ -92,7 +93,7 @@ class ASyncSwitchEnv:
         self.rail_map = RailMap(rail_env.fixture)
         self.possible_agents = self.rail_map.tab.switch_names()          # switch_env.py:51-52
         self.agents = self.possible_agents
-        kw = dict(act_cap=1)
+        kw = dict(act_cap=1, shared_q=shared_q)
         kw.update(_engine_kwargs or {})
         self.engine = Engine(self.rail_map, n_envs=self.n_envs, device=device, q_cap=q_cap, max_steps=max_steps, ep_cap=ep_cap, **kw)
         # the seven wall-clock accumulators main.py:72-78 prints (switch_env.py:67-73); the device loop has no
@@ -200,7 +201,7 @@ class DistrQLearning:
     """Batched counterpart of distr_q.py:11-527."""
 
     def __init__(self, env: ASyncSwitchEnv, gamma=1.0, epsilon=0.4, epsilon_decay_rate=0.0, lr=0.4, lr_decay_rate=0.0,
-                 default_q=0.0, seed=450565, seeds: Optional[Sequence[int]] = None):
+                 default_q=0.0, seed=450565, seeds: Optional[Sequence[int]] = None, dist=None):
         self.env = env
         self.gamma, self.initial_epsilon, self.epsilon_decay_rate = gamma, epsilon, epsilon_decay_rate
         self.initial_lr, self.lr_decay_rate, self.default_q = lr, lr_decay_rate, default_q
@@ -208,6 +209,7 @@ class DistrQLearning:
         self.seeds = (np.asarray(seeds, np.uint64) if seeds is not None
                       else np.arange(env.n_envs, dtype=np.uint64) + np.uint64(seed))
         self.ticks_per_launch = 512
+        self.dist = dist                       # torch.distributed (initialised) for the shared-table all-reduce, else None
         self.primary_env = 0                 # the env whose curves / Q-table go to the reference-named files
         self.q_table: Dict[tuple, List[float]] = {}
         self.total_decisions = 0
@@ -221,11 +223,19 @@ class DistrQLearning:
                                     lr=self.initial_lr, lr_decay_rate=self.lr_decay_rate, default_q=self.default_q,
                                     seeds=self.seeds, episodes=episodes, episode_base=episode_base)
 
+    def _begin_tables(self, keep_q: bool):
+        """Shared-table mode (extension): the one table of this engine replaces the per-environment tables."""
+        eng = self.env.engine
+        if eng.shared_q and not keep_q:
+            eng.init_shared_q(self._default_q_of(0), q_init=True)
+
     def _run_until_halted(self, mode: int) -> np.ndarray:
         eng = self.env.engine
         t0 = time.time()
         while True:
             eng.run(mode, self.ticks_per_launch)
+            if eng.shared_q and mode == MODE_LEARN:
+                eng.shared_q_sync(self.dist)       # every ticks_per_launch ticks: fold the mean TD steps into the table
             c = eng.counters()
             if c["err"].any():
                 eng.check_errors()
@@ -256,11 +266,14 @@ class DistrQLearning:
             self._hparams(-1)
             eng.reset()
             eng.enable_q_init(True)
+            self._begin_tables(False)
             self._q_inited = True
             self._stream_fresh = False
         else:
             eng._upload("hparams", eng.hparams)
         eng.run(MODE_LEARN, self.ticks_per_launch if max_ticks is None else max_ticks)
+        if eng.shared_q:
+            eng.shared_q_sync(self.dist)
         return eng.counters()
 
     # ------------------------------------------------------------------ distr_q.py:244-379
@@ -288,6 +301,7 @@ class DistrQLearning:
                 if first:
                     t0 = time.time()
                     eng.reset(keep_q=self._table_dirty, keep_interactions=False)     # agent_num_interactions is per learn() (:263)
+                    self._begin_tables(self._table_dirty)
                     if self._table_dirty:
                         self._apply_q_init_to_existing_rows()
                     eng.enable_q_init(True)                                           # distr_q.py:299-300

@@ -44,18 +44,19 @@ class MapDesc(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_envs", "q_cap", "pend_cap", "max_steps", "dec_cap", "tick_cap", "ep_cap",
-                                         "act_cap", "ev_cap", "trace_sem")]
+                                         "act_cap", "ev_cap", "trace_sem", "shared_q")]
 
 
 class Sizes(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("state_bytes", "env_stride", "hparams_bytes", "trace_dec_bytes", "trace_tick_bytes",
                                           "trace_sem_bytes", "ep_log_bytes", "ep_delay_bytes", "replay_act_bytes",
-                                          "replay_ev_bytes", "counters_bytes", "step_out_bytes")] + [("q_stride", C.c_int32), ("a_max", C.c_int32)]
+                                          "replay_ev_bytes", "counters_bytes", "step_out_bytes", "shared_q_bytes", "shared_d_bytes",
+                                          "shared_c_bytes")] + [("q_stride", C.c_int32), ("a_max", C.c_int32)]
 
 
 class Buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("state", "hparams", "counters", "trace_dec", "trace_tick", "trace_sem", "ep_log",
-                                          "ep_delay", "replay_act", "replay_ev", "step_out")]
+                                          "ep_delay", "replay_act", "replay_ev", "step_out", "shared_q", "shared_d", "shared_c")]
 
 
 HPARAMS_DT = np.dtype([("gamma", "f8"), ("epsilon", "f8"), ("epsilon_decay_rate", "f8"), ("lr", "f8"), ("lr_decay_rate", "f8"),
@@ -92,7 +93,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sfl_total_decisions.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
     lib.sfl_export_q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.c_void_p]
     lib.sfl_import_q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_int, C.c_void_p]
-    if lib.sfl_abi_version() != 3:
+    lib.sfl_shared_q_apply.argtypes = [C.c_void_p, C.c_void_p]
+    if lib.sfl_abi_version() != 4:
         raise RuntimeError("switchfl_b200 ABI version mismatch")
     return lib
 
@@ -193,7 +195,8 @@ class Engine:
 
     def __init__(self, rail_map: RailMap, n_envs: int, device: str = "cuda:0", q_cap: int = 1024, pend_cap: int = 8,
                  max_steps: int = 100_000, dec_cap: int = 0, tick_cap: int = 0, ep_cap: int = 64, act_cap: int = 0,
-                 ev_cap: int = 0, trace_sem: bool = False, lanes: Optional[int] = None, _emul_lib: Optional[str] = None):
+                 ev_cap: int = 0, trace_sem: bool = False, lanes: Optional[int] = None, shared_q: bool = False,
+                 _emul_lib: Optional[str] = None):
         import torch
         self.torch = torch
         self.map = rail_map
@@ -210,7 +213,9 @@ class Engine:
             self.device = torch.device(device)
             dev_index = self.device.index or 0
         self.cfg = Config(n_envs=self.n_envs, q_cap=q_cap, pend_cap=pend_cap, max_steps=max_steps, dec_cap=dec_cap,
-                          tick_cap=tick_cap, ep_cap=ep_cap, act_cap=act_cap, ev_cap=ev_cap, trace_sem=int(trace_sem))
+                          tick_cap=tick_cap, ep_cap=ep_cap, act_cap=act_cap, ev_cap=ev_cap, trace_sem=int(trace_sem),
+                          shared_q=int(shared_q))
+        self.shared_q = bool(shared_q)
         self.sizes = Sizes()
         self._ck(self.lib.sfl_query_sizes(C.byref(rail_map.desc), C.byref(self.cfg), C.byref(self.sizes)))
         self.ctx = C.c_void_p()
@@ -220,7 +225,8 @@ class Engine:
         self.buf = {"state": z(s.state_bytes), "hparams": z(s.hparams_bytes), "counters": z(s.counters_bytes),
                     "trace_dec": z(s.trace_dec_bytes), "trace_tick": z(s.trace_tick_bytes), "trace_sem": z(s.trace_sem_bytes),
                     "ep_log": z(s.ep_log_bytes), "ep_delay": z(s.ep_delay_bytes), "replay_act": z(s.replay_act_bytes),
-                    "replay_ev": z(s.replay_ev_bytes), "step_out": z(s.step_out_bytes)}
+                    "replay_ev": z(s.replay_ev_bytes), "step_out": z(s.step_out_bytes), "shared_q": z(s.shared_q_bytes),
+                    "shared_d": z(s.shared_d_bytes), "shared_c": z(s.shared_c_bytes)}
         b = Buffers(**{k: v.data_ptr() for k, v in self.buf.items()})
         self._ck(self.lib.sfl_bind(self.ctx, C.byref(b)))
         if lanes is not None:
@@ -313,6 +319,57 @@ class Engine:
                 ev[i, :len(e)] = e
             self._upload("replay_ev", ev)
 
+    # ------------------------------------------------------------------ shared-table mode (extension)
+    def _shared_cells(self) -> int:
+        return self.map.tab.NP * len(self.map.trains.targets) * 48 * self.sizes.a_max
+
+    def init_shared_q(self, default_q: float = 0.0, q_init: bool = True):
+        """Fill the shared table: default_q everywhere, the optimistic rows of distr_q.py:81-181 when ``q_init``."""
+        assert self.shared_q
+        t, tr = self.map.tab, self.map.trains
+        NT, a_max = len(tr.targets), self.sizes.a_max
+        q = np.full((t.NP, NT, 16, 3, a_max), float(default_q), np.float64)
+        if q_init:
+            port, tgt = np.nonzero(np.asarray(tr.qinit_act) >= 0)
+            act = np.asarray(tr.qinit_act)[port, tgt]
+            val = np.asarray(tr.qinit_val)[port, tgt]
+            for semb in range(1, 16):                                   # every semaphore vector except all-red (:98-125)
+                q[port, tgt, semb, :, act] = val[:, None]
+        self._upload("shared_q", q)
+        self.buf["shared_d"].zero_()
+        self.buf["shared_c"].zero_()
+
+    def shared_q_sync(self, dist=None):
+        """Fold the accumulated TD steps into the table; with an initialised ``torch.distributed`` first sum the
+        accumulators over all ranks (integer all-reduce: NCCL on the GPU box, gloo in the CPU tests)."""
+        assert self.shared_q
+        if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+            n = self._shared_cells()
+            d = self.buf["shared_d"][:n * 8].view(self.torch.int64)
+            c = self.buf["shared_c"][:n * 4].view(self.torch.int32)
+            dist.all_reduce(d, op=dist.ReduceOp.SUM)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        self._ck(self.lib.sfl_shared_q_apply(self.ctx, self._stream()))
+
+    def shared_q_table(self) -> np.ndarray:
+        """The shared table as float64[NP, NT, 16 semaphore vectors, 3 delay levels, a_max]."""
+        t, tr = self.map.tab, self.map.trains
+        n = self._shared_cells()
+        return self._download("shared_q", n * 8).view(np.float64).reshape(t.NP, len(tr.targets), 16, 3, self.sizes.a_max).copy()
+
+    def export_shared_q(self, default_q: float = 0.0) -> Dict[tuple, List[float]]:
+        """Rows of the shared table that differ from ``default_q`` somewhere, in the reference's dict layout."""
+        q = self.shared_q_table()
+        t = self.map.tab
+        out = {}
+        for port, tgt, semb, level in zip(*np.nonzero((q != float(default_q)).any(axis=-1))):
+            s_ = int(t.port_switch[port])
+            if semb >> int(t.sw_P[s_]):
+                continue                                                # bits beyond the switch's ports are never produced
+            key = ((int(port) * q.shape[1] + int(tgt)) * 16 + int(semb)) * 3 + int(level)
+            out[self.map.key_to_obs(key)] = [float(x) for x in q[port, tgt, semb, level, :int(t.sw_A[s_])]]
+        return out
+
     # ------------------------------------------------------------------ host-driven AEC protocol (SFL_MODE_STEP)
     def step(self, actions: Optional[Sequence[int]] = None, max_ticks: Optional[int] = None) -> np.ndarray:
         """Apply ``actions[i]`` to the decision waiting in env i (ignored where none waits), advance every env to
@@ -366,6 +423,8 @@ class Engine:
 
     def export_q(self, env: int, include_init: bool = False, default_q: Optional[float] = None) -> Dict[tuple, List[float]]:
         """The reference's q_table dict (distr_q.py:42, pickled by :521-523): obs tuple -> list of A floats."""
+        if self.shared_q:
+            return self.export_shared_q(float(self.hparams["default_q"][env]) if default_q is None else default_q)
         a_max = self.sizes.a_max
         cap = self.cfg.q_cap
         keys = np.zeros(cap, np.uint32)

@@ -110,6 +110,14 @@ __global__ void k_sum(const sfl_env_counters *c, int n, unsigned long long *out)
   if ((threadIdx.x & 31) == 0) { atomicAdd(out, d); atomicAdd(out + 1, t); }
 }
 
+// shared-table mode: fold the mean proposed step into the table, clear the accumulators
+__global__ void k_shared_apply(double *q, long long *d, int *c, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = c[i];
+    if (k) { q[i] += (double)d[i] / 16777216.0 / (double)k; d[i] = 0; c[i] = 0; }
+  }
+}
+
 typedef void (*run_kernel_t)();
 template <int G> static run_kernel_t pick_kernel_g(int trace, int th) {
   if (trace) return th ? k_run<G, true, true> : k_run<G, true, false>;
@@ -210,6 +218,8 @@ int sfl_query_sizes(const sfl_map_desc *map, const sfl_config *cfg, sfl_sizes *o
   out->hparams_bytes = B * sizeof(sfl_hparams);
   out->counters_bytes = B * sizeof(sfl_env_counters);
   out->step_out_bytes = B * sizeof(sfl_step_rec);
+  const uint64_t cells = cfg->shared_q ? (uint64_t)map->NP * map->NT * 48ull * (uint64_t)a_max : 0;
+  out->shared_q_bytes = cells * 8ull; out->shared_d_bytes = cells * 8ull; out->shared_c_bytes = cells * 4ull;
   out->trace_dec_bytes = B * (uint64_t)cfg->dec_cap * sizeof(sfl_dec_rec);
   out->trace_tick_bytes = B * (uint64_t)cfg->tick_cap * map->T * sizeof(sfl_tick_rec);
   out->trace_sem_bytes = cfg->trace_sem ? B * (uint64_t)cfg->dec_cap * map->NP * 16ull : 0;
@@ -357,6 +367,7 @@ int sfl_bind(void *ctx, const sfl_buffers *bufs) {
   if (!bufs->state || !bufs->hparams || !bufs->counters) return fail(SFL_E_ARG, "state, hparams and counters are mandatory%s");
   if (c->cfg.dec_cap > 0 && !bufs->trace_dec) return fail(SFL_E_ARG, "dec_cap > 0 needs trace_dec%s");
   if (c->cfg.tick_cap > 0 && !bufs->trace_tick) return fail(SFL_E_ARG, "tick_cap > 0 needs trace_tick%s");
+  if (c->cfg.shared_q && (!bufs->shared_q || !bufs->shared_d || !bufs->shared_c)) return fail(SFL_E_ARG, "shared_q needs the three shared buffers%s");
   c->bufs = *bufs;
   c->bound = 1;
   return SFL_OK;
@@ -424,6 +435,7 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   ra.ep_delay = c->cfg.ep_cap > 0 ? (int *)c->bufs.ep_delay : nullptr;
   ra.replay_act = (const int8_t *)c->bufs.replay_act;
   ra.step_out = (sfl_step_rec *)c->bufs.step_out;
+  if (c->cfg.shared_q) { ra.sq_q = (double *)c->bufs.shared_q; ra.sq_d = (long long *)c->bufs.shared_d; ra.sq_c = (int *)c->bufs.shared_c; }
   // recorded malfunction events replace the Philox draws in replay mode, and in greedy / step mode when a schedule was bound (ev_cap > 0)
   ra.replay_ev = (mode != SFL_MODE_LEARN && c->cfg.ev_cap > 0) ? (const int *)c->bufs.replay_ev : nullptr;
   const int trace = ra.trace_dec || ra.trace_tick || mode == SFL_MODE_STEP;      // the step protocol lives in the trace kernels
@@ -446,6 +458,22 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   for (int i = 0; i < c->cfg.n_envs; i++) {
     if (trace) env_run<1, true, true>(i, 0u, host_scratch); else env_run<1, false, true>(i, 0u, host_scratch);
   }
+#endif
+  return SFL_OK;
+}
+
+int sfl_shared_q_apply(void *ctx, void *stream) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || !c->bound) return fail(SFL_E_STATE, "sfl_bind first%s");
+  if (!c->cfg.shared_q) return fail(SFL_E_STATE, "context was not created in shared-table mode%s");
+  const size_t n = (size_t)c->m.NP * c->m.NT * 48u * (size_t)c->L.a_max;
+  double *q = (double *)c->bufs.shared_q; long long *d = (long long *)c->bufs.shared_d; int *cn = (int *)c->bufs.shared_c;
+#ifndef SFL_HOST_EMUL
+  k_shared_apply<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(q, d, cn, n);
+  CU(cudaGetLastError());
+#else
+  (void)stream;
+  for (size_t i = 0; i < n; i++) if (cn[i]) { q[i] += (double)d[i] / 16777216.0 / (double)cn[i]; d[i] = 0; cn[i] = 0; }
 #endif
   return SFL_OK;
 }

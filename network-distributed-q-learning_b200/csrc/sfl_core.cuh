@@ -156,6 +156,7 @@ struct RunArgs {           // per-launch arguments
   sfl_dec_rec *trace_dec; sfl_tick_rec *trace_tick; int4 *trace_sem_buf;
   sfl_ep_rec *ep_log; int *ep_delay;
   sfl_step_rec *step_out;
+  double *sq_q; long long *sq_d; int *sq_c;           // shared-table mode (null otherwise): table, delta sums (2^-24), delta counts
   const int8_t *replay_act; const int *replay_ev;     // ev: [env][ev_cap][3] = (tick, train, duration), tick-sorted, tick<0 ends
 };
 
@@ -276,6 +277,7 @@ SFL_FN int port_blocked(Env e, int next_port, int out_port, int me, int now) {
 // key set equals the reference's.
 template <class Env>
 SFL_NI double *q_row(Env e, const sfl_hparams *hp, unsigned key) {
+  if (c_ra.sq_q) return c_ra.sq_q + (size_t)key * c_L.a_max;            // shared-table mode: dense, initialised by the host
   unsigned mask = (unsigned)c_L.q_cap - 1u;
   unsigned i = (key * 2654435761u) >> 7;
   SFL_NU
@@ -308,6 +310,13 @@ SFL_NI double *q_row(Env e, const sfl_hparams *hp, unsigned key) {
   return e.q() + 1;     // keep running on row 0 (flagged)
 }
 
+// integer sums: the accumulated step does not depend on the order in which the environments arrive
+#if SFL_DEV
+SFL_FN void shared_add(long long *d, int *c, long long v) { atomicAdd((unsigned long long *)d, (unsigned long long)v); atomicAdd(c, 1); }
+#else
+SFL_FN void shared_add(long long *d, int *c, long long v) { *d += v; *c += 1; }
+#endif
+
 // lr * lr_decay_rate ** n (distr_q.py:70-79): pow only off the shipped-config path (every script uses rate 1.0)
 SFL_NI double lr_pow(double rate, int n) { return pow(rate, (double)n); }
 
@@ -320,6 +329,20 @@ SFL_NI void q_update(Env e, const sfl_hparams *hp, unsigned key, int action, dou
   if (hp->lr_decay_rate != 1.0) lr = dmul(lr, lr_pow(hp->lr_decay_rate, e.sws()[prev_sw].ninter));
   double one_m = dadd(1.0, -lr);
   double q = row[action];
+  if (c_ra.sq_q) {                                                       // shared table: propose the TD step, leave the table alone
+    double mq = 0.0;
+    if (next_sw != prev_sw && next_row) {
+      int A = c_m.sw[next_sw].y;
+      mq = next_row[0];
+      SFL_NU
+      for (int a = 1; a < A; a++) { const double v = next_row[a]; mq = v > mq ? v : mq; }
+    }
+    const double nq = next_sw != prev_sw ? dadd(dmul(one_m, q), dmul(lr, dadd(reward, dmul(hp->gamma, mq))))
+                                         : dadd(dmul(one_m, q), dmul(lr, reward));
+    const size_t i = (size_t)key * c_L.a_max + action;
+    shared_add(c_ra.sq_d + i, c_ra.sq_c + i, (long long)llrint((nq - q) * 16777216.0));
+    return;
+  }
   if (next_sw != prev_sw) {
     double mq = 0.0;
     if (next_row) {                                             // distr_q.py:449-466 max_q ignores the mask

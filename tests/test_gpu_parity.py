@@ -257,3 +257,28 @@ def test_cuda_learn_c4_size_properties():
     c2 = eng.counters()
     assert np.array_equal(c2["decisions"], first["decisions"]) and np.array_equal(c2["aborted"], first["aborted"])
     eng.close()
+
+
+def test_cuda_shared_table_mode_matches_the_host_build_properties():
+    """Shared-table mode (extension): atomics on the device, integer accumulation -> bit-reproducible and equal to a
+    single-environment run when all environments are identical."""
+    fx, _ = load_golden("slips24_t6")
+    rm = backend.RailMap(fx)
+    hp = dict(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0)
+
+    def run(seeds):
+        eng = gpu_engine(rm, n_envs=len(seeds), q_cap=2, ep_cap=4, shared_q=True)
+        eng.set_hparams(**hp, seeds=seeds, episodes=-1)
+        eng.reset()
+        eng.init_shared_q(0.0)
+        for _ in range(5):
+            eng.run(backend.MODE_LEARN, 64)
+            eng.check_errors()
+            eng.shared_q_sync()
+        q = eng.shared_q_table()
+        eng.close()
+        return q
+    q1 = run([7])
+    assert np.array_equal(q1, run([7] * 64))
+    qa, qb = run(list(range(1, 200))), run(list(range(1, 200)))
+    assert np.array_equal(qa, qb) and np.isfinite(qa).all() and not np.array_equal(qa, q1)

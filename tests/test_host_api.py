@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol(product_lib):
     assert {"sfl_create", "sfl_run", "sfl_reset", "sfl_bind", "sfl_export_q", "sfl_import_q", "sfl_query_sizes"} <= set(names)
     for n in names:
         assert hasattr(product_lib, n), f"{n} declared in include/switchfl_b200.h but not exported"
-    assert product_lib.sfl_abi_version() == 3
+    assert product_lib.sfl_abi_version() == 4
 
 
 def test_struct_layouts_match_the_header():
@@ -267,3 +267,81 @@ def test_grid_launcher_writes_the_reference_tree():
             assert set(c["MODEL"]) == {"gamma", "epsilon", "epsilon_decay_rate", "lr", "lr_decay_rate", "default_q", "num_episodes"}
             assert np.load(os.path.join(d, "cum_reward.npz"))["x"].shape == (3,)
             assert isinstance(pickle.load(open(os.path.join(d, "distr_q_model.pkl"), "rb")), dict)
+
+
+# ---------------------------------------------------------------------------------------------- shared-table mode (extension)
+HP_SHARED = dict(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0)
+
+
+def _shared_run(rm, emul, seeds, launches=5, ticks=64, dist=None):
+    eng = backend.Engine(rm, n_envs=len(seeds), q_cap=2, ep_cap=4, shared_q=True, _emul_lib=emul)
+    eng.set_hparams(**HP_SHARED, seeds=seeds, episodes=-1)
+    eng.reset()
+    eng.init_shared_q(0.0)
+    for _ in range(launches):
+        eng.run(backend.MODE_LEARN, ticks)
+        eng.check_errors()
+        eng.shared_q_sync(dist)
+    return eng
+
+
+def test_shared_table_mode_is_deterministic_and_averages():
+    """No reference counterpart (BASELINE config 5): properties of the policy stated in DESIGN.md.  Integer
+    accumulation makes the result independent of the order in which environments arrive; N identical environments
+    propose N identical steps whose mean is the step, so they leave the table a single environment leaves."""
+    emul = build_emul()
+    fx, _ = load_golden("slips24_t6")
+    rm = backend.RailMap(fx)
+    one = _shared_run(rm, emul, [7])
+    q1 = one.shared_q_table()
+    assert np.array_equal(q1, _shared_run(rm, emul, [7]).shared_q_table())
+    assert np.array_equal(q1, _shared_run(rm, emul, [7, 7, 7, 7]).shared_q_table())
+    mixed = _shared_run(rm, emul, [1, 2, 3, 4, 5, 6])
+    qm = mixed.shared_q_table()
+    assert np.isfinite(qm).all() and not np.array_equal(qm, q1)
+    init = backend.Engine(rm, n_envs=1, q_cap=2, shared_q=True, _emul_lib=emul)
+    init.init_shared_q(0.0)
+    q0 = init.shared_q_table()
+    assert set(np.unique(q0)) <= {0.0, 500.0, 1000.0} and (q0 == 500.0).any()             # distr_q.py:44-45, 156-181
+    learned = mixed.export_q(0)
+    assert learned and all(len(k) in (14, 18) for k in learned)
+    # the environments keep no private rows in this mode
+    assert (mixed.counters()["q_rows"] == 0).all()
+
+
+_SHARED_WORKER = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from __graft_entry__ import load_package
+load_package()
+import torch.distributed as dist
+from switchfl_b200 import backend, mapgen, sharding
+sys.path.insert(0, os.path.join(sys.argv[1]))
+from tests.test_host_api import _shared_run
+rank, ws, _ = sharding.world()
+dist.init_process_group("gloo", rank=rank, world_size=ws)
+fx = mapgen.load_fixture(os.path.join(sys.argv[1], "tests", "golden", "slips24_t6.fixture.npz"))
+rm = backend.RailMap(fx)
+lo, hi = sharding.shard_range(6, rank, ws)
+eng = _shared_run(rm, sys.argv[2], list(range(1 + lo, 1 + hi)), dist=dist)
+np.save(os.path.join(sys.argv[3], f"q{rank}.npy"), eng.shared_q_table())
+dist.destroy_process_group()
+'''
+
+
+def test_shared_table_two_ranks_allreduce_equals_one_process():
+    """Two ranks with three environments each, accumulators all-reduced (gloo) before every apply: both ranks end with
+    the table one process with all six environments ends with, bit for bit."""
+    emul = build_emul()
+    fx, _ = load_golden("slips24_t6")
+    rm = backend.RailMap(fx)
+    want = _shared_run(rm, emul, [1, 2, 3, 4, 5, 6]).shared_q_table()
+    with tempfile.TemporaryDirectory() as tmp:
+        w = os.path.join(tmp, "w.py")
+        open(w, "w").write(_SHARED_WORKER)
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                              "--master-port", "29543", w, ROOT, emul, tmp], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        q0, q1 = np.load(os.path.join(tmp, "q0.npy")), np.load(os.path.join(tmp, "q1.npy"))
+    assert np.array_equal(q0, q1) and np.array_equal(q0, want)
