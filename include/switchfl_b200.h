@@ -161,6 +161,13 @@ typedef struct sfl_ep_rec {            /* one finished episode (distr_q.py:360-3
   uint64_t arrived_mask;               /* the trains at their destination ("arrived_trains", :345, 371) */
 } sfl_ep_rec;
 
+/* Distance map (flatland DistanceMap as vendored in flatland_patch/distance_map.py:62-167):
+ * dist[k][r][c][heading] = moves from (cell, heading) to target_cells[k], 0x3FFFFFFF if unreachable; all four headings
+ * of a target cell are 0.  Host pointers in and out (one-off map preprocessing); computed on `device` by one CTA per
+ * target relaxing d(cell, o) = 1 + min over the exits h of (cell, o) of d(cell + step(h), h) to its fixed point.     */
+int sfl_distance_map(const uint16_t *grid, int32_t H, int32_t W, const int32_t *target_cells, int32_t n_targets,
+                     int32_t *dist, int device);
+
 int sfl_abi_version(void);
 const char *sfl_last_error(void);
 

@@ -90,11 +90,13 @@ class ASyncSwitchEnv:
         self.render_mode = render_mode
         self.seed = seed
         self.n_envs = int(n_envs)
-        self.rail_map = RailMap(rail_env.fixture)
-        self.possible_agents = self.rail_map.tab.switch_names()          # switch_env.py:51-52
-        self.agents = self.possible_agents
         kw = dict(act_cap=1, shared_q=shared_q)
         kw.update(_engine_kwargs or {})
+        import torch
+        on_gpu = "_emul_lib" not in kw and torch.cuda.is_available()
+        self.rail_map = RailMap(rail_env.fixture, device_bfs=(torch.device(device).index or 0) if on_gpu else None)
+        self.possible_agents = self.rail_map.tab.switch_names()          # switch_env.py:51-52
+        self.agents = self.possible_agents
         self.engine = Engine(self.rail_map, n_envs=self.n_envs, device=device, q_cap=q_cap, max_steps=max_steps, ep_cap=ep_cap, **kw)
         # the seven wall-clock accumulators main.py:72-78 prints (switch_env.py:67-73); the device loop has no
         # per-phase split, so the kernel time is booked on step_time and resets on reset_total_time

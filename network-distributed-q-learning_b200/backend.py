@@ -94,9 +94,24 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sfl_export_q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.c_void_p]
     lib.sfl_import_q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_int, C.c_void_p]
     lib.sfl_shared_q_apply.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sfl_distance_map.argtypes = [_u16p, C.c_int32, C.c_int32, _i32p, C.c_int32, _i32p, C.c_int]
     if lib.sfl_abi_version() != 4:
         raise RuntimeError("switchfl_b200 ABI version mismatch")
     return lib
+
+
+def device_distance_map(grid: np.ndarray, target_cells: Sequence[int], device: int = 0, _emul_lib: Optional[str] = None) -> np.ndarray:
+    """int32[NT, H, W, 4] distance map of flatland_patch/distance_map.py:62-167 computed on the GPU (``sfl_distance_map``);
+    same values as the host BFS ``railmap.distance_to`` (which the goldens pin against the vendored reference code)."""
+    lib = load_library(_emul_lib)
+    g = np.ascontiguousarray(grid, np.uint16)
+    tg = np.ascontiguousarray(target_cells, np.int32)
+    H, W = g.shape
+    out = np.empty((len(tg), H, W, 4), np.int32)
+    rc = lib.sfl_distance_map(g.ctypes.data_as(_u16p), H, W, tg.ctypes.data_as(_i32p), len(tg), out.ctypes.data_as(_i32p), int(device))
+    if rc != 0:
+        raise RuntimeError(f"switchfl_b200 error {rc}: {lib.sfl_last_error().decode()}")
+    return out
 
 
 def malf_threshold(rate: float) -> int:
@@ -109,11 +124,13 @@ def malf_threshold(rate: float) -> int:
 class RailMap:
     """Everything derived from one fixture: port-graph tables, per-train constants, the C descriptor."""
 
-    def __init__(self, fixture: dict):
+    def __init__(self, fixture: dict, device_bfs: Optional[int] = None):
+        """``device_bfs``: CUDA device index to compute the distance map with ``sfl_distance_map`` (None: host BFS)."""
         self.fixture = fixture
         self.tab = railmap.build_switch_tables(fixture["grid"])
+        dist_fn = None if device_bfs is None else (lambda grid, cells: device_distance_map(grid, cells, device=device_bfs))
         self.trains = railmap.build_train_tables(self.tab, fixture["init_pos"], fixture["init_dir"], fixture["target"],
-                                                 fixture["earliest_departure"], fixture["latest_arrival"])
+                                                 fixture["earliest_departure"], fixture["latest_arrival"], dist_fn=dist_fn)
         t, tr = self.tab, self.trains
         self._keep = {}
 

@@ -118,6 +118,42 @@ __global__ void k_shared_apply(double *q, long long *d, int *c, size_t n) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ distance map (row F6 / N1)
+// d(cell, o) = 0 on the target cell, else 1 + min over the exits h of (cell, o) of d(cell + step(h), h): unit-cost
+// shortest paths, i.e. the reverse BFS of flatland_patch/distance_map.py:88-167, as a monotone relaxation to the fixed
+// point.  One CTA per target; the table of the target lives in shared memory when it fits (SMEM), else in the output.
+template <bool SMEM>
+__global__ void __launch_bounds__(512) k_distance_map(const uint16_t *grid, int H, int W, const int *targets, int *out) {
+  extern __shared__ int s_dist[];
+  const int n = H * W * 4, target = targets[blockIdx.x];
+  int *gd = out + (size_t)blockIdx.x * n;
+  int *d = SMEM ? s_dist : gd;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = (i >> 2) == target ? 0 : SFL_INF_DIST;
+  __syncthreads();
+  for (;;) {
+    int changed = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int cell = i >> 2, o = i & 3;
+      if (cell == target) continue;
+      const unsigned nib = ((unsigned)grid[cell] >> ((3 - o) * 4)) & 0xFu;       // exits of heading o, bit (3 - h)
+      if (!nib) continue;
+      const int r = cell / W, c = cell - r * W;
+      int best = ((volatile int *)d)[i];
+#pragma unroll
+      for (int h = 0; h < 4; h++) {
+        if (!((nib >> (3 - h)) & 1u)) continue;
+        const int nr = r + (h == 0 ? -1 : h == 2 ? 1 : 0), nc = c + (h == 1 ? 1 : h == 3 ? -1 : 0);
+        if (nr < 0 || nr >= H || nc < 0 || nc >= W) continue;
+        const int v = ((volatile int *)d)[(nr * W + nc) * 4 + h];
+        if (v < SFL_INF_DIST && v + 1 < best) best = v + 1;
+      }
+      if (best < ((volatile int *)d)[i]) { d[i] = best; changed = 1; }
+    }
+    if (!__syncthreads_or(changed)) break;
+  }
+  if (SMEM) for (int i = threadIdx.x; i < n; i += blockDim.x) gd[i] = d[i];
+}
+
 typedef void (*run_kernel_t)();
 template <int G> static run_kernel_t pick_kernel_g(int trace, int th) {
   if (trace) return th ? k_run<G, true, true> : k_run<G, true, false>;
@@ -205,6 +241,60 @@ static int set_constants(const Ctx *c, const RunArgs *ra, void *stream) {
 extern "C" {
 
 int sfl_abi_version(void) { return SFL_ABI_VERSION; }
+
+int sfl_distance_map(const uint16_t *grid, int32_t H, int32_t W, const int32_t *target_cells, int32_t n_targets, int32_t *dist, int device) {
+  if (!grid || !target_cells || !dist || H < 1 || W < 1 || n_targets < 0) return fail(SFL_E_ARG, "bad argument%s");
+  const size_t n = (size_t)H * W * 4;
+  for (int k = 0; k < n_targets; k++) if (target_cells[k] < 0 || target_cells[k] >= H * W) return fail(SFL_E_ARG, "target outside the grid%s");
+  if (!n_targets) return SFL_OK;
+#ifndef SFL_HOST_EMUL
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SFL_E_CUDA, "no CUDA device: this library has no CPU path%s");
+  CU(cudaSetDevice(device));
+  uint16_t *dg = nullptr; int *dt = nullptr, *dd = nullptr;
+  if (cudaMalloc(&dg, (size_t)H * W * 2) != cudaSuccess || cudaMalloc(&dt, (size_t)n_targets * 4) != cudaSuccess ||
+      cudaMalloc(&dd, n * 4 * n_targets) != cudaSuccess) { cudaFree(dg); cudaFree(dt); cudaFree(dd); return fail(SFL_E_CUDA, "device alloc failed%s"); }
+  int rc = SFL_OK;
+  do {
+    if (cudaMemcpy(dg, grid, (size_t)H * W * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(dt, target_cells, (size_t)n_targets * 4, cudaMemcpyHostToDevice) != cudaSuccess) { rc = fail(SFL_E_CUDA, "upload failed%s"); break; }
+    const size_t smem = n * 4;
+    if (smem <= 200u * 1024u) {
+      if (cudaFuncSetAttribute(k_distance_map<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { rc = fail(SFL_E_CUDA, "smem attribute%s"); break; }
+      k_distance_map<true><<<n_targets, 512, smem>>>(dg, H, W, dt, dd);
+    } else {
+      k_distance_map<false><<<n_targets, 512, 0>>>(dg, H, W, dt, dd);
+    }
+    if (cudaGetLastError() != cudaSuccess || cudaMemcpy(dist, dd, n * 4 * n_targets, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(SFL_E_CUDA, "distance map kernel failed%s");
+  } while (0);
+  cudaFree(dg); cudaFree(dt); cudaFree(dd);
+  return rc;
+#else
+  (void)device;
+  for (int k = 0; k < n_targets; k++) {                                  // the same relaxation, one thread
+    int *d = dist + (size_t)k * n;
+    const int target = target_cells[k];
+    for (size_t i = 0; i < n; i++) d[i] = (int)(i >> 2) == target ? 0 : SFL_INF_DIST;
+    for (int changed = 1; changed;) {
+      changed = 0;
+      for (int i = 0; i < (int)n; i++) {
+        const int cell = i >> 2, o = i & 3;
+        if (cell == target) continue;
+        const unsigned nib = ((unsigned)grid[cell] >> ((3 - o) * 4)) & 0xFu;
+        const int r = cell / W, c = cell - r * W;
+        for (int h = 0; h < 4; h++) {
+          if (!((nib >> (3 - h)) & 1u)) continue;
+          const int nr = r + (h == 0 ? -1 : h == 2 ? 1 : 0), nc = c + (h == 1 ? 1 : h == 3 ? -1 : 0);
+          if (nr < 0 || nr >= H || nc < 0 || nc >= W) continue;
+          const int v = d[(nr * W + nc) * 4 + h];
+          if (v < SFL_INF_DIST && v + 1 < d[i]) { d[i] = v + 1; changed = 1; }
+        }
+      }
+    }
+  }
+  return SFL_OK;
+#endif
+}
 const char *sfl_last_error(void) { return g_err; }
 
 int sfl_query_sizes(const sfl_map_desc *map, const sfl_config *cfg, sfl_sizes *out) {

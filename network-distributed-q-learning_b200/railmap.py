@@ -417,7 +417,7 @@ class TrainTables:
     qinit_val: np.ndarray        # float64[NP, NT] 500. or 1000.
 
 
-def build_train_tables(tab: SwitchTables, init_pos, init_dir, target, ed, la) -> TrainTables:
+def build_train_tables(tab: SwitchTables, init_pos, init_dir, target, ed, la, dist_fn=None) -> TrainTables:
     grid, H, W = tab.grid, tab.H, tab.W
     T = len(init_dir)
     init_pos = np.asarray(init_pos, np.int64).reshape(T, 2)
@@ -435,7 +435,11 @@ def build_train_tables(tab: SwitchTables, init_pos, init_dir, target, ed, la) ->
             targets.append(tc)
         tgt_index[i] = targets.index(tc)
     NT = len(targets)
-    dist = np.stack([distance_to(grid, (tc // W, tc % W)) for tc in targets]) if NT else np.zeros((0, H, W, 4), np.int32)
+    # ``dist_fn(grid, target_cells) -> int32[NT,H,W,4]``: the device BFS (backend.device_distance_map) when a GPU is there
+    if NT and dist_fn is not None:
+        dist = np.asarray(dist_fn(grid, targets), np.int32)
+    else:
+        dist = np.stack([distance_to(grid, (tc // W, tc % W)) for tc in targets]) if NT else np.zeros((0, H, W, 4), np.int32)
     first_port = np.zeros(T, np.int32); first_dist = np.zeros(T, np.int32); init_delay = np.zeros(T, np.int32)
     for i in range(T):
         r, c, d = int(init_pos[i, 0]), int(init_pos[i, 1]), int(init_dir[i])

@@ -232,3 +232,16 @@ def test_emul_fuzz_maps_against_oracle(i, emul_lib):
         pytest.skip(str(ex))
     check_against_oracle(lambda rm, **kw: backend.Engine(rm, _emul_lib=emul_lib, **kw), fx, hp, 3, seeds, max_steps=max_steps,
                          greedy_after=True, q_cap=16384)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_emul_distance_map_matches_vendored_reference(name, emul_lib):
+    """Row F6: the relaxation of sfl_distance_map against the distance map recorded from the reference's vendored
+    flatland_patch/distance_map.py (golden field ``dist``, per train) and against the host BFS."""
+    import numpy as np
+    from tests._util import load_golden
+    fx, g = load_golden(name)
+    rm = backend.RailMap(fx)
+    d = backend.device_distance_map(fx["grid"], rm.trains.targets, _emul_lib=emul_lib)
+    assert np.array_equal(d, rm.trains.dist)
+    assert np.array_equal(d[rm.trains.tgt_index], g["dist"])                 # golden: one map per train handle

@@ -282,3 +282,23 @@ def test_cuda_shared_table_mode_matches_the_host_build_properties():
     assert np.array_equal(q1, run([7] * 64))
     qa, qb = run(list(range(1, 200))), run(list(range(1, 200)))
     assert np.array_equal(qa, qb) and np.isfinite(qa).all() and not np.array_equal(qa, q1)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_distance_map_matches_vendored_reference(name):
+    """Row F6 / N1: the k_distance_map kernel against the vendored flatland_patch/distance_map.py (golden ``dist``)."""
+    fx, g = load_golden(name)
+    rm = backend.RailMap(fx)
+    d = backend.device_distance_map(fx["grid"], rm.trains.targets)
+    assert np.array_equal(d, rm.trains.dist)
+    assert np.array_equal(d[rm.trains.tgt_index], g["dist"])
+
+
+def test_cuda_distance_map_large_grid_uses_the_global_memory_variant():
+    """A 240x240 grid (921 KB of states per target) does not fit shared memory."""
+    from switchfl_b200 import railmap
+    fx = mapgen.make_fixture(240, 6, 60, seed=9, num_cities=12)
+    cells = [int(r) * 240 + int(c) for r, c in fx["target"]]
+    d = backend.device_distance_map(fx["grid"], cells)
+    for k, (r, c) in enumerate(fx["target"]):
+        assert np.array_equal(d[k], railmap.distance_to(fx["grid"], (int(r), int(c)))), k
