@@ -98,7 +98,8 @@ typedef struct sfl_hparams {
   int32_t malf_min, malf_max;   /* duration = min + U{0..max-min} + 1                                 */
   int32_t episodes;             /* halt after this many episodes since sfl_reset (<0: never)          */
   int32_t episode_base;         /* global index of the first episode after sfl_reset (RNG stream offset) */
-  int32_t reserved;
+  uint32_t malf_thr2;           /* floor(malf_threshold * 256 / ceil(malf_threshold / 2^24)): stage-2 threshold of the
+                                   two-stage malfunction draw; 0 when malf_threshold is 0  */
 } sfl_hparams;
 
 /* byte sizes of the caller-owned buffers for a (map, config) pair */

@@ -61,7 +61,7 @@ class Buffers(C.Structure):
 
 HPARAMS_DT = np.dtype([("gamma", "f8"), ("epsilon", "f8"), ("epsilon_decay_rate", "f8"), ("lr", "f8"), ("lr_decay_rate", "f8"),
                        ("default_q", "f8"), ("seed", "u8"), ("malf_threshold", "u4"), ("malf_min", "i4"), ("malf_max", "i4"),
-                       ("episodes", "i4"), ("episode_base", "i4"), ("reserved", "i4")])
+                       ("episodes", "i4"), ("episode_base", "i4"), ("malf_thr2", "u4")])
 COUNTERS_DT = np.dtype([("decisions", "u8"), ("ticks", "u8"), ("train_ticks", "u8"), ("episodes", "i4"), ("err", "i4"),
                         ("q_rows", "i4"), ("halted", "i4"), ("n_dec_logged", "i4"), ("n_tick_logged", "i4"),
                         ("n_ep_logged", "i4"), ("elapsed", "i4"), ("aborted", "i4"), ("reserved", "i4")])
@@ -119,6 +119,14 @@ def malf_threshold(rate: float) -> int:
     if rate <= 0:
         return 0
     return min(int((1.0 - math.exp(-rate)) * 4294967296.0), 0xFFFFFFFF)
+
+
+def malf_thr2(threshold: int) -> int:
+    """Stage-2 threshold of the two-stage malfunction draw: floor(thr * 256 / B) with B = ceil(thr / 2^24)."""
+    if threshold <= 0:
+        return 0
+    b = (threshold + 0xFFFFFF) >> 24
+    return min((threshold << 8) // b, 0xFFFFFFFF)
 
 
 class RailMap:
@@ -303,6 +311,7 @@ class Engine:
         hp["seed"] = np.arange(self.n_envs, dtype=np.uint64) if seeds is None else np.asarray(seeds, np.uint64)
         rate = fx["malfunction_rate"] if malfunction_rate is None else malfunction_rate
         hp["malf_threshold"] = malf_threshold(float(rate))
+        hp["malf_thr2"] = malf_thr2(int(hp["malf_threshold"][0]))
         hp["malf_min"] = fx["min_duration"] if min_duration is None else min_duration
         hp["malf_max"] = fx["max_duration"] if max_duration is None else max_duration
         self._upload("hparams", hp)
@@ -428,9 +437,9 @@ class Engine:
     def trace(self, env: int):
         c = self.counters()[env]
         T, NP = self.map.trains.T, self.map.tab.NP
-        dec = self._download("trace_dec").view(DEC_DT)[:self.n_envs * self.cfg.dec_cap].reshape(self.n_envs, self.cfg.dec_cap)[env]
+        dec = self._download("trace_dec", self.n_envs * self.cfg.dec_cap * DEC_DT.itemsize).view(DEC_DT).reshape(self.n_envs, self.cfg.dec_cap)[env]
         dec = dec[:min(int(c["n_dec_logged"]), self.cfg.dec_cap)]
-        tick = self._download("trace_tick").view(TICK_DT)[:self.n_envs * self.cfg.tick_cap * T].reshape(self.n_envs, self.cfg.tick_cap, T)[env]
+        tick = self._download("trace_tick", self.n_envs * self.cfg.tick_cap * T * TICK_DT.itemsize).view(TICK_DT).reshape(self.n_envs, self.cfg.tick_cap, T)[env]
         tick = tick[:min(int(c["n_tick_logged"]), self.cfg.tick_cap)]
         sem = None
         if self.cfg.trace_sem:

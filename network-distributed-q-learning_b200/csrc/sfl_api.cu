@@ -96,11 +96,11 @@ __global__ void __launch_bounds__(SFL_CTA_THREADS) k_init(InitArgs ia) {
 // environment: [hot env state (hot_bytes) | sfl_hparams | Scratch]; the hot state (header, train records, pending
 // lists and -- when they fit -- semaphores, rewards and per-switch counters) is staged once per launch and written
 // back at the end, so the tick / decision loops touch HBM only for Q rows.
-template <int G, bool TRACE, bool TH>
+template <int G, bool TRACE, bool TH, bool SQ>
 __global__ void __launch_bounds__(SFL_CTA_THREADS, TH ? (G == 32 ? 7 : 4) : SFL_MINB_BIG) k_run() {
   const int slot = threadIdx.x / G;                    // environment slot inside the CTA
   const int env_id = blockIdx.x * (blockDim.x / G) + slot;
-  env_run<G, TRACE, TH>(env_id, (unsigned)slot * c_ra.env_smem, nullptr);
+  env_run<G, TRACE, TH, SQ>(env_id, (unsigned)slot * c_ra.env_smem, nullptr);
 }
 
 __global__ void k_sum(const sfl_env_counters *c, int n, unsigned long long *out) {
@@ -155,18 +155,19 @@ __global__ void __launch_bounds__(512) k_distance_map(const uint16_t *grid, int 
 }
 
 typedef void (*run_kernel_t)();
-template <int G> static run_kernel_t pick_kernel_g(int trace, int th) {
-  if (trace) return th ? k_run<G, true, true> : k_run<G, true, false>;
-  return th ? k_run<G, false, true> : k_run<G, false, false>;
+template <int G> static run_kernel_t pick_kernel_g(int trace, int th, int sq) {
+  if (sq) return th ? k_run<G, false, true, true> : k_run<G, false, false, true>;       // shared-table variants: no tracing
+  if (trace) return th ? k_run<G, true, true, false> : k_run<G, true, false, false>;
+  return th ? k_run<G, false, true, false> : k_run<G, false, false, false>;
 }
-static run_kernel_t pick_kernel(int G, int trace, int th) {
+static run_kernel_t pick_kernel(int G, int trace, int th, int sq) {
   switch (G) {
-    case 1: return pick_kernel_g<1>(trace, th);
-    case 2: return pick_kernel_g<2>(trace, th);
-    case 4: return pick_kernel_g<4>(trace, th);
-    case 8: return pick_kernel_g<8>(trace, th);
-    case 16: return pick_kernel_g<16>(trace, th);
-    default: return pick_kernel_g<32>(trace, th);
+    case 1: return pick_kernel_g<1>(trace, th, sq);
+    case 2: return pick_kernel_g<2>(trace, th, sq);
+    case 4: return pick_kernel_g<4>(trace, th, sq);
+    case 8: return pick_kernel_g<8>(trace, th, sq);
+    case 16: return pick_kernel_g<16>(trace, th, sq);
+    default: return pick_kernel_g<32>(trace, th, sq);
   }
 }
 #endif
@@ -537,7 +538,8 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   const size_t smem = (size_t)c->env_smem * envs_per_cta;
   if (smem > 227u * 1024u) return fail(SFL_E_ARG, "environment state does not fit shared memory with this many lanes per env: use more lanes%s");
   int grid = (c->cfg.n_envs + envs_per_cta - 1) / envs_per_cta;
-  run_kernel_t k = pick_kernel(G, trace, (int)c->tail_hot);
+  if (c->cfg.shared_q && trace) return fail(SFL_E_ARG, "shared-table mode has no trace / step variants%s");
+  run_kernel_t k = pick_kernel(G, trace, (int)c->tail_hot, c->cfg.shared_q);
   CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(set_constants(c, &ra, stream));
   k<<<grid, threads, smem, (cudaStream_t)stream>>>();
@@ -546,7 +548,11 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   static char host_scratch[32 * SFL_MAX_T + 2 * SFL_MAX_T + 64];
   set_constants(c, &ra, stream);
   for (int i = 0; i < c->cfg.n_envs; i++) {
-    if (trace) env_run<1, true, true>(i, 0u, host_scratch); else env_run<1, false, true>(i, 0u, host_scratch);
+    if (c->cfg.shared_q) {
+      if (trace) return fail(SFL_E_ARG, "shared-table mode has no trace / step variants%s");
+      env_run<1, false, true, true>(i, 0u, host_scratch);
+    } else if (trace) env_run<1, true, true, false>(i, 0u, host_scratch);
+    else env_run<1, false, true, false>(i, 0u, host_scratch);
   }
 #endif
   return SFL_OK;

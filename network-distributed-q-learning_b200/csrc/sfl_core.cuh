@@ -68,6 +68,7 @@ template <int G> struct Grp {
   }
   SFL_FN void sync() const { __syncwarp(); }
   SFL_FN int wany(int p) const { return __any_sync(0xffffffffu, p); }          // over the warp
+  SFL_FN unsigned wor(unsigned v) const { return __reduce_or_sync(0xffffffffu, v); }   // over the warp (one REDUX)
   // bit i = predicate of the group's lane i
   SFL_FN unsigned ballot(int p) const {
     unsigned b = __ballot_sync(0xffffffffu, p);
@@ -87,6 +88,7 @@ template <int G> struct Grp {
   Grp() : gl(0), shift(0) {}
   void sync() const {}
   int wany(int p) const { return p; }
+  unsigned wor(unsigned v) const { return v; }
   unsigned ballot(int p) const { return p ? 1u : 0u; }
   int any(int p) const { return p; }
 };
@@ -177,7 +179,10 @@ SFL_FN char *hot_ptr(hot_t o) { return o; }
 #endif
 
 // TH ("tail hot"): semaphores, rewards and per-switch records are part of the staged block; else they stay in HBM / L2
-template <bool TH> struct EnvT {
+// SQ ("shared Q"): the shared-table extension; a compile-time variant, because even an untaken runtime branch in the
+// Q-row functions cost the private-table kernels 20-25 % on large maps (registers / code size at 72 registers)
+template <bool TH, bool SQ_ = false> struct EnvT {
+  static const bool SQ = SQ_;
   hot_t hot;               // staged copy of the first hot_bytes of the env block (the env block itself on the host build)
   char *gb;                // the env block in HBM
   SFL_FN EnvHdr *h() const { return (EnvHdr *)hot_ptr(hot); }
@@ -199,7 +204,7 @@ struct Scratch {
   int8_t *occ;             // [T] train standing on my destination cell, or -1
   uint8_t *blk;            // [T] movement blocked
   int *inj;                // [T] replay only: injected malfunction durations of this tick
-  int4 *rng;               // [T] the four malfunction words of the current 4-tick block (one Philox call per train and block)
+  int4 *rng;               // [T] the 16 stage-1 malfunction bytes of the current 16-tick block (one Philox call per train and block)
 };
 #if SFL_DEV
 __host__
@@ -277,7 +282,7 @@ SFL_FN int port_blocked(Env e, int next_port, int out_port, int me, int now) {
 // key set equals the reference's.
 template <class Env>
 SFL_NI double *q_row(Env e, const sfl_hparams *hp, unsigned key) {
-  if (c_ra.sq_q) return c_ra.sq_q + (size_t)key * c_L.a_max;            // shared-table mode: dense, initialised by the host
+  if (Env::SQ) return c_ra.sq_q + (size_t)key * c_L.a_max;              // shared-table mode: dense, initialised by the host
   unsigned mask = (unsigned)c_L.q_cap - 1u;
   unsigned i = (key * 2654435761u) >> 7;
   SFL_NU
@@ -329,7 +334,7 @@ SFL_NI void q_update(Env e, const sfl_hparams *hp, unsigned key, int action, dou
   if (hp->lr_decay_rate != 1.0) lr = dmul(lr, lr_pow(hp->lr_decay_rate, e.sws()[prev_sw].ninter));
   double one_m = dadd(1.0, -lr);
   double q = row[action];
-  if (c_ra.sq_q) {                                                       // shared table: propose the TD step, leave the table alone
+  if (Env::SQ) {                                                         // shared table: propose the TD step, leave the table alone
     double mq = 0.0;
     if (next_sw != prev_sw && next_row) {
       int A = c_m.sw[next_sw].y;
@@ -686,18 +691,22 @@ SFL_FN void env_reset(Env e, const Grp<G> &g, int on) {
 // Group-uniform registers carried across the ticks of a launch (every lane of the group holds the same values);
 // the header copy in shared memory is what the decision phase (first lane) reads and writes.
 struct TickRegs {
-  int elapsed, ended, rng_blk;                 // rng_blk: 4-tick block the cached malfunction words belong to (-1: none)
+  int elapsed, ended, rng_blk;                 // rng_blk: 16-tick block the cached malfunction bytes belong to (-1: none)
   unsigned long long active, done, malf_prev;
   unsigned long long ticks, train_ticks;       // launch-local, added to the header at the end
 };
 
-// Malfunction draw of train t at tick `now` (row F5): one Philox4x32-10 call per (train, 4-tick block), one 32-bit word
-// per tick.  Event iff word < threshold (probability 1 - exp(-rate)); given an event the word is uniform below the
-// threshold, which gives the duration min + U{0..max-min} + 1 without a second word.
-SFL_FN int malf_duration(const sfl_hparams *hp, unsigned w) {
-  if (w >= hp->malf_threshold) return 0;
-  unsigned range = (unsigned)(hp->malf_max - hp->malf_min + 1);
-  return hp->malf_min + (int)(((unsigned long long)w * range) / hp->malf_threshold) + 1;
+// Malfunction draw of train t at tick `now` (row F5), probability thr / 2^32 = 1 - exp(-rate) per (train, tick), in two
+// stages so that the common no-event tick costs one byte compare:
+//   stage 1  one Philox4x32-10 call per (train, 16-tick block), counter (tick >> 4, train, 0xA11F, 0): 16 bytes, byte
+//            tick & 15 is a candidate iff it is below B = ceil(thr / 2^24)                         (probability B / 256)
+//   stage 2  candidates only: Philox counter (tick, train, 0xA11E, 0); event iff word 0 < thr2 = floor(thr * 256 / B)
+//            (sfl_hparams.malf_thr2; probability thr2 / 2^32, product = thr / 2^32); word 1 gives the duration
+//            min + U{0..max-min} + 1.
+SFL_FN int malf_stage2(const sfl_hparams *hp, int now, int t) {
+  const U4 u = philox4x32((unsigned)now, (unsigned)t, 0xA11Eu, 0u, (unsigned)hp->seed, (unsigned)(hp->seed >> 32));
+  if (u.x >= hp->malf_thr2) return 0;
+  return hp->malf_min + (int)(((unsigned long long)u.y * (unsigned)(hp->malf_max - hp->malf_min + 1)) >> 32) + 1;
 }
 
 template <int G, bool TRACE, class Env>
@@ -723,7 +732,8 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
     }
     g.sync();
   }
-  const int fresh_rng = !replay_ev && thr && (now >> 2) != R.rng_blk;    // group-uniform
+  const int fresh_rng = !replay_ev && thr && (now >> 4) != R.rng_blk;    // group-uniform
+  const unsigned coarse = (thr >> 24) + ((thr & 0xFFFFFFu) ? 1u : 0u);   // stage-1 byte threshold B
   // ---- phase A: per train: plan pop (switch_env.py:304-339) + flatland step part 1 (Appendix B step 2)
   SFL_NU
   for (int t = g.gl; t < T; t += G) {
@@ -737,10 +747,10 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
     if (replay_ev) dur = sc.inj[t];
     else if (thr) {
       if (fresh_rng) {
-        U4 u = philox4x32((unsigned)(now >> 2), (unsigned)t, 0xA11Fu, 0u, (unsigned)hp->seed, (unsigned)(hp->seed >> 32));
+        U4 u = philox4x32((unsigned)(now >> 4), (unsigned)t, 0xA11Fu, 0u, (unsigned)hp->seed, (unsigned)(hp->seed >> 32));
         sc.rng[t] = make_int4((int)u.x, (int)u.y, (int)u.z, (int)u.w);
       }
-      dur = malf_duration(hp, ((const unsigned *)&sc.rng[t])[now & 3]);
+      if (((const uint8_t *)&sc.rng[t])[now & 15] < coarse) dur = malf_stage2(hp, now, t);
     }
     if (mc == 0 && dur > 0) mc = dur;
     int src, dst, ecell = -1, nd = d, act = A_NOTHING, a = A_NOTHING, flags = 0;
@@ -771,7 +781,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
     e.tra()[t] = ta;
     sc.tmp[t] = make_int4(src, dst, ecell, nd | (act << 8) | (a << 16) | (flags << 24));
   }
-  if (fresh_rng) R.rng_blk = now >> 2;
+  if (fresh_rng) R.rng_blk = now >> 4;
   g.sync();
   // ---- phase B: motion check (F3)
   unsigned long long chain = 0;               // trains whose destination is occupied by a train that is itself moving
@@ -1006,14 +1016,14 @@ SFL_FN void step_report(Env e, int env_id, int t) {
   o->elapsed = h->elapsed; o->last_next_sw = h->last_next_sw; o->arrived = h->done_mask;
 }
 
-template <int G, bool TRACE, bool TH>
+template <int G, bool TRACE, bool TH, bool SQ>
 SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
   const Grp<G> g;
   const int valid = env_id < c_ra.n_envs;                                 // idle slots of the last warp keep the warp's rendezvous
   if (!valid) env_id = 0;
   char *gbase = c_ra.state + (size_t)env_id * c_L.env_stride;
   const unsigned hot_bytes = valid ? c_ra.hot_bytes : 0u;
-  EnvT<TH> e;
+  EnvT<TH, SQ> e;
   const sfl_hparams *hp;
   Scratch sc;
   e.gb = gbase;
@@ -1057,11 +1067,13 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
     g.sync();
     if (live) R.ended = h->terminated | h->truncated;
   }
+  int any_reset = g.wany(live && need_reset);                             // warp-uniform; can only change in a decision phase
   SFL_NU
   for (int it = 0; it < c_ra.max_ticks; it++) {
-    if (!g.wany(live && !paused)) break;                                  // warp-uniform
     const int due = live && !paused && (R.active || R.ended);             // something is due before the tick
-    if (g.wany(due)) {
+    const unsigned wf = g.wor((live && !paused ? 1u : 0u) | (due ? 2u : 0u));   // one warp-wide OR: anybody running / due
+    if (!(wf & 1u)) break;
+    if (wf & 2u) {
       if (due && g.gl == 0 && stepping) {
         if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<TRACE>(e, hp, env_id);
         int t = -1;
@@ -1081,12 +1093,14 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
       }
       g.sync();
       if (due) { need_reset = h->need_reset; R.active = 0; if (stepping) paused = h->cur_train >= 0; }
+      any_reset = g.wany(live && need_reset);
     }
-    if (g.wany(live && need_reset)) {
+    if (any_reset) {
       if (live && need_reset && hp->episodes >= 0 && h->episode >= hp->episodes) live = 0;      // halt: need_reset stays set
       const int on = live && need_reset;
       env_reset<G>(e, g, on);
       if (on) { need_reset = 0; R.elapsed = 0; R.ended = 0; R.rng_blk = -1; R.active = 0; R.done = 0; R.malf_prev = 0; }
+      any_reset = 0;
     }
     env_tick<G, TRACE>(e, sc, hp, env_id, g, R, live && !paused);
   }

@@ -245,3 +245,32 @@ def test_emul_distance_map_matches_vendored_reference(name, emul_lib):
     d = backend.device_distance_map(fx["grid"], rm.trains.targets, _emul_lib=emul_lib)
     assert np.array_equal(d, rm.trains.dist)
     assert np.array_equal(d[rm.trains.tgt_index], g["dist"])                 # golden: one map per train handle
+
+
+def test_emul_malfunction_draws_have_the_flatland_distribution(emul_lib):
+    """Row F5 in free-running mode (two-stage Philox draw): per (train, tick) an event with probability 1 - exp(-rate),
+    duration uniform on {min..max} + 1 (ParamMalfunctionGen)."""
+    import numpy as np
+    from tests._util import load_golden
+    fx, _ = load_golden("c1_synth18")                                     # rate 0.01, durations 5..15
+    rm = backend.RailMap(fx)
+    B, T = 8192, 2
+    eng = backend.Engine(rm, n_envs=B, q_cap=64, ep_cap=2, tick_cap=60, _emul_lib=emul_lib)
+    eng.set_hparams(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0,
+                    seeds=np.arange(B) * 7919 + 5, episodes=1)
+    eng.reset()
+    eng.enable_q_init(True)
+    eng.run(backend.MODE_LEARN, 100)
+    tick = eng._download("trace_tick", B * 60 * T * 8).view(backend.TICK_DT).reshape(B, 60, T)
+    n = eng.counters()["n_tick_logged"]
+    m = tick["malf"].astype(int)
+    valid = np.arange(60)[None, :, None] < n[:, None, None]
+    prev = np.concatenate([np.zeros((B, 1, T), int), m[:, :-1]], axis=1)
+    draws = ((prev == 0) & valid).sum()
+    new = (prev == 0) & (m > 0) & valid
+    p = 1.0 - np.exp(-0.01)
+    assert abs(new.sum() / draws - p) < 4 * np.sqrt(p / draws)
+    durs = np.bincount(m[new] + 1, minlength=17)
+    assert durs[:6].sum() == 0 and len(durs) == 17                         # 5..15 + 1
+    expect = new.sum() / 11
+    assert (np.abs(durs[6:17] - expect) < 5 * np.sqrt(expect)).all()
