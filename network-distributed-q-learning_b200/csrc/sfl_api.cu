@@ -96,11 +96,11 @@ __global__ void __launch_bounds__(SFL_CTA_THREADS) k_init(InitArgs ia) {
 // environment: [hot env state (hot_bytes) | sfl_hparams | Scratch]; the hot state (header, train records, pending
 // lists and -- when they fit -- semaphores, rewards and per-switch counters) is staged once per launch and written
 // back at the end, so the tick / decision loops touch HBM only for Q rows.
-template <int G, bool TRACE, bool TH, bool SQ>
+template <int G, int KIND, bool TH, bool SQ>
 __global__ void __launch_bounds__(SFL_CTA_THREADS, TH ? (G == 32 ? 7 : 4) : SFL_MINB_BIG) k_run() {
   const int slot = threadIdx.x / G;                    // environment slot inside the CTA
   const int env_id = blockIdx.x * (blockDim.x / G) + slot;
-  env_run<G, TRACE, TH, SQ>(env_id, (unsigned)slot * c_ra.env_smem, nullptr);
+  env_run<G, KIND, TH, SQ>(env_id, (unsigned)slot * c_ra.env_smem, nullptr);
 }
 
 __global__ void k_sum(const sfl_env_counters *c, int n, unsigned long long *out) {
@@ -155,19 +155,23 @@ __global__ void __launch_bounds__(512) k_distance_map(const uint16_t *grid, int 
 }
 
 typedef void (*run_kernel_t)();
-template <int G> static run_kernel_t pick_kernel_g(int trace, int th, int sq) {
-  if (sq) return th ? k_run<G, false, true, true> : k_run<G, false, false, true>;       // shared-table variants: no tracing
-  if (trace) return th ? k_run<G, true, true, false> : k_run<G, true, false, false>;
-  return th ? k_run<G, false, true, false> : k_run<G, false, false, false>;
+template <int G> static run_kernel_t pick_kernel_g(int kind, int th, int sq) {
+  if (sq) {                                                                              // shared-table variants: learn / greedy only
+    if (kind == K_GREEDY) return th ? k_run<G, K_GREEDY, true, true> : k_run<G, K_GREEDY, false, true>;
+    return th ? k_run<G, K_LEARN, true, true> : k_run<G, K_LEARN, false, true>;
+  }
+  if (kind == K_FULL) return th ? k_run<G, K_FULL, true, false> : k_run<G, K_FULL, false, false>;
+  if (kind == K_GREEDY) return th ? k_run<G, K_GREEDY, true, false> : k_run<G, K_GREEDY, false, false>;
+  return th ? k_run<G, K_LEARN, true, false> : k_run<G, K_LEARN, false, false>;
 }
-static run_kernel_t pick_kernel(int G, int trace, int th, int sq) {
+static run_kernel_t pick_kernel(int G, int kind, int th, int sq) {
   switch (G) {
-    case 1: return pick_kernel_g<1>(trace, th, sq);
-    case 2: return pick_kernel_g<2>(trace, th, sq);
-    case 4: return pick_kernel_g<4>(trace, th, sq);
-    case 8: return pick_kernel_g<8>(trace, th, sq);
-    case 16: return pick_kernel_g<16>(trace, th, sq);
-    default: return pick_kernel_g<32>(trace, th, sq);
+    case 1: return pick_kernel_g<1>(kind, th, sq);
+    case 2: return pick_kernel_g<2>(kind, th, sq);
+    case 4: return pick_kernel_g<4>(kind, th, sq);
+    case 8: return pick_kernel_g<8>(kind, th, sq);
+    case 16: return pick_kernel_g<16>(kind, th, sq);
+    default: return pick_kernel_g<32>(kind, th, sq);
   }
 }
 #endif
@@ -529,7 +533,9 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   if (c->cfg.shared_q) { ra.sq_q = (double *)c->bufs.shared_q; ra.sq_d = (long long *)c->bufs.shared_d; ra.sq_c = (int *)c->bufs.shared_c; }
   // recorded malfunction events replace the Philox draws in replay mode, and in greedy / step mode when a schedule was bound (ev_cap > 0)
   ra.replay_ev = (mode != SFL_MODE_LEARN && c->cfg.ev_cap > 0) ? (const int *)c->bufs.replay_ev : nullptr;
-  const int trace = ra.trace_dec || ra.trace_tick || mode == SFL_MODE_STEP;      // the step protocol lives in the trace kernels
+  // learn and greedy without traces run the two specialised kernels; replay, step and traced runs the full one
+  const int trace = ra.trace_dec || ra.trace_tick || mode == SFL_MODE_STEP || mode == SFL_MODE_REPLAY;
+  const int kind = trace ? K_FULL : (mode == SFL_MODE_GREEDY ? K_GREEDY : K_LEARN);
 #ifndef SFL_HOST_EMUL
   const int G = c->lanes;
   int threads = SFL_CTA_THREADS;                       // shrink the CTA until its environments fit shared memory
@@ -539,7 +545,7 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   if (smem > 227u * 1024u) return fail(SFL_E_ARG, "environment state does not fit shared memory with this many lanes per env: use more lanes%s");
   int grid = (c->cfg.n_envs + envs_per_cta - 1) / envs_per_cta;
   if (c->cfg.shared_q && trace) return fail(SFL_E_ARG, "shared-table mode has no trace / step variants%s");
-  run_kernel_t k = pick_kernel(G, trace, (int)c->tail_hot, c->cfg.shared_q);
+  run_kernel_t k = pick_kernel(G, kind, (int)c->tail_hot, c->cfg.shared_q);
   CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(set_constants(c, &ra, stream));
   k<<<grid, threads, smem, (cudaStream_t)stream>>>();
@@ -550,9 +556,10 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   for (int i = 0; i < c->cfg.n_envs; i++) {
     if (c->cfg.shared_q) {
       if (trace) return fail(SFL_E_ARG, "shared-table mode has no trace / step variants%s");
-      env_run<1, false, true, true>(i, 0u, host_scratch);
-    } else if (trace) env_run<1, true, true, false>(i, 0u, host_scratch);
-    else env_run<1, false, true, false>(i, 0u, host_scratch);
+      if (kind == K_GREEDY) env_run<1, K_GREEDY, true, true>(i, 0u, host_scratch); else env_run<1, K_LEARN, true, true>(i, 0u, host_scratch);
+    } else if (kind == K_FULL) env_run<1, K_FULL, true, false>(i, 0u, host_scratch);
+    else if (kind == K_GREEDY) env_run<1, K_GREEDY, true, false>(i, 0u, host_scratch);
+    else env_run<1, K_LEARN, true, false>(i, 0u, host_scratch);
   }
 #endif
   return SFL_OK;

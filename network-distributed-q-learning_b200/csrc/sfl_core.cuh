@@ -217,6 +217,13 @@ SFL_FN Scratch make_scratch(char *p, int T) {
   return s;
 }
 
+// ------------------------------------------------------------------------------------------------ kernel kinds
+// The run mode is a compile-time property of the two production kernels (learn, greedy): with the mode a runtime
+// value the replay / step / trace paths stayed in the hot kernels and cost the large-map kernels 8 % (registers and
+// instruction fetch at 72 registers).  The third kind carries everything: any mode, traces, the step protocol.
+enum { K_LEARN = 0, K_GREEDY = 1, K_FULL = 2 };
+template <int KIND> SFL_FN int run_mode() { return KIND == K_LEARN ? (int)SFL_MODE_LEARN : KIND == K_GREEDY ? (int)SFL_MODE_GREEDY : c_ra.mode; }
+
 // ------------------------------------------------------------------------------------------------ Philox4x32-10
 struct U4 { unsigned x, y, z, w; };
 SFL_FN unsigned mulhi32(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
@@ -322,8 +329,14 @@ SFL_FN void shared_add(long long *d, int *c, long long v) { atomicAdd((unsigned 
 SFL_FN void shared_add(long long *d, int *c, long long v) { *d += v; *c += 1; }
 #endif
 
-// lr * lr_decay_rate ** n (distr_q.py:70-79): pow only off the shipped-config path (every script uses rate 1.0)
-SFL_NI double lr_pow(double rate, int n) { return pow(rate, (double)n); }
+// lr_decay_rate ** n (distr_q.py:70-79) by binary exponentiation: at most 2 log2(n) roundings (~1e-15 relative, the
+// parity bar off the shipped configs is 1e-12; every script uses rate 1.0, which is exact) and none of pow()'s code
+SFL_FN double lr_pow(double rate, int n) {
+  double r = 1.0, b = rate;
+  SFL_NU
+  for (; n > 0; n >>= 1) { if (n & 1) r = dmul(r, b); b = dmul(b, b); }
+  return r;
+}
 
 // distr_q.py:419-447 update (fp64, Python operator order, no FMA contraction)
 template <class Env>
@@ -432,10 +445,12 @@ SFL_FN int delay_at(Env e, int tgt_index, int cell, int dir, int now, int la) {
 
 // the tail of one iteration of distr_q.py:302-362 that must wait for the train ticks run inside env.step()
 // (switch_env.py:648-649): arrival flush (:345-356), interaction counter (:362), truncation (switch_env.py:652-657)
-template <bool TRACE, class Env>
+template <int KIND, class Env>
 SFL_FN void finish_decision(Env e, const sfl_hparams *hp, int env_id) {
+  const bool TRACE = KIND == K_FULL;
+  const int mode = run_mode<KIND>();
   EnvHdr *h = e.h();
-  if (c_ra.mode == SFL_MODE_LEARN || c_ra.mode == SFL_MODE_REPLAY) {
+  if (mode == SFL_MODE_LEARN || mode == SFL_MODE_REPLAY) {
     unsigned long long fresh = h->done_mask & ~h->at_dest_mask;
     SFL_NU
     while (fresh) {
@@ -508,8 +523,10 @@ SFL_FN Obs observe(Env e, int t, int now, const int4 ta, const int4 tb) {
 }
 
 // one switch-agent decision: observe (O1-O3) -> act (Q1) -> apply (E2, E3, R1) -> Q-update (Q2, Q3)
-template <bool TRACE, class Env>
+template <int KIND, class Env>
 SFL_FN void decide(Env e, const sfl_hparams *hp, int env_id, int t) {
+  const bool TRACE = KIND == K_FULL;
+  const int mode = run_mode<KIND>();
   EnvHdr *h = e.h();
   const int now = h->elapsed;
   int4 ta = e.tra()[t], tb = e.trb()[t];
@@ -527,25 +544,25 @@ SFL_FN void decide(Env e, const sfl_hparams *hp, int env_id, int t) {
   const int my_port = (int)((unsigned)ta.w >> 16);
   const int reward_in = e.rewards()[s * c_L.T + t];                               // last(): _cumulative_rewards[agent][train]
   // ---- act (distr_q.py:312-320 / :211)
-  const int learning = c_ra.mode == SFL_MODE_LEARN || c_ra.mode == SFL_MODE_REPLAY;
+  const int learning = mode == SFL_MODE_LEARN || mode == SFL_MODE_REPLAY;
   double *my_row = nullptr;
   int action = -1;
-  if (c_ra.mode == SFL_MODE_REPLAY || c_ra.mode == SFL_MODE_STEP) {
-    if (c_ra.mode == SFL_MODE_STEP) h->act_cursor = 0;         // the host's action for this decision
+  if (mode == SFL_MODE_REPLAY || mode == SFL_MODE_STEP) {
+    if (mode == SFL_MODE_STEP) h->act_cursor = 0;              // the host's action for this decision
     int exploited = 0;
     if (h->act_cursor >= c_ra.act_cap) { h->err |= SFL_ERR_REPLAY_UNDERRUN; action = A - 1; }
     else {
       action = c_ra.replay_act[(size_t)env_id * c_ra.act_cap + h->act_cursor++];
       // bit 6 of a recorded action: the learner exploited, i.e. max_action was consulted -- which inserts the row
       // (distr_q.py:318-319, 482); the replay then also checks that the recorded action IS the argmax
-      if (c_ra.mode == SFL_MODE_REPLAY && action >= 0 && (action & 0x40)) { exploited = 1; action &= 0x3F; }
+      if (mode == SFL_MODE_REPLAY && action >= 0 && (action & 0x40)) { exploited = 1; action &= 0x3F; }
     }
     if (action < 0 || action >= A) { h->err |= SFL_ERR_BAD_ACTION; action = A - 1; }
     if (exploited) {
       my_row = q_row(e, hp, key);
       if (max_action(my_row, A, mask) != action) h->err |= SFL_ERR_REPLAY_DIVERGED;
     }
-  } else if (c_ra.mode == SFL_MODE_LEARN) {
+  } else if (mode == SFL_MODE_LEARN) {
     double eps = dmul(hp->epsilon, e.sws()[s].eps_pow);
     U4 u = philox4x32((unsigned)h->step_counter, (unsigned)(hp->episode_base + h->episode), 0x5F1u, 0u, (unsigned)hp->seed, (unsigned)(hp->seed >> 32));
     double u01 = ((double)u.x + 0.5) * (1.0 / 4294967296.0);
@@ -709,15 +726,16 @@ SFL_FN int malf_stage2(const sfl_hparams *hp, int now, int t) {
   return hp->malf_min + (int)(((unsigned long long)u.y * (unsigned)(hp->malf_max - hp->malf_min + 1)) >> 32) + 1;
 }
 
-template <int G, bool TRACE, class Env>
+template <int G, int KIND, class Env>
 // `live` = this group's environment takes part (not halted, not an idle slot of the last warp); every loop bound and
 // branch that contains a collective is warp-uniform, the per-group work inside is predicated.
 SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const Grp<G> &g, TickRegs &R, const int live) {
+  const bool TRACE = KIND == K_FULL;
   EnvHdr *h = e.h();
   const int Tw = c_L.T;                                                  // warp-uniform loop bound
   const int T = live ? Tw : 0;
   const int now = R.elapsed + 1;                                         // flatland: _elapsed_steps += 1 first
-  const int replay_ev = c_ra.replay_ev != 0;
+  const int replay_ev = KIND != K_LEARN && c_ra.replay_ev != 0;          // recorded events never replace the draws in learn mode
   const unsigned thr = live ? hp->malf_threshold : 0u;
   if (replay_ev) {
     SFL_NU
@@ -1016,8 +1034,9 @@ SFL_FN void step_report(Env e, int env_id, int t) {
   o->elapsed = h->elapsed; o->last_next_sw = h->last_next_sw; o->arrived = h->done_mask;
 }
 
-template <int G, bool TRACE, bool TH, bool SQ>
+template <int G, int KIND, bool TH, bool SQ>
 SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
+  const bool TRACE = KIND == K_FULL;
   const Grp<G> g;
   const int valid = env_id < c_ra.n_envs;                                 // idle slots of the last warp keep the warp's rendezvous
   if (!valid) env_id = 0;
@@ -1057,11 +1076,11 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
     R.active = h->active_mask; R.done = h->done_mask; R.malf_prev = h->malf_prev_mask;
     need_reset = h->need_reset; live = !h->halted;
   }
-  const int stepping = TRACE && c_ra.mode == SFL_MODE_STEP;
+  const int stepping = TRACE && run_mode<KIND>() == SFL_MODE_STEP;
   int paused = 0;                                                         // stepping: a decision waits for the host
   if (stepping) {
     if (live && g.gl == 0) {
-      if (h->cur_train >= 0) { decide<TRACE>(e, hp, env_id, h->cur_train); h->cur_train = -1; }
+      if (h->cur_train >= 0) { decide<KIND>(e, hp, env_id, h->cur_train); h->cur_train = -1; }
       else h->last_next_sw = -1;
     }
     g.sync();
@@ -1075,7 +1094,7 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
     if (!(wf & 1u)) break;
     if (wf & 2u) {
       if (due && g.gl == 0 && stepping) {
-        if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<TRACE>(e, hp, env_id);
+        if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<KIND>(e, hp, env_id);
         int t = -1;
         if (!(h->terminated || h->truncated) && h->active_mask) { t = ffs64(h->active_mask); h->active_mask &= h->active_mask - 1; }
         step_report(e, env_id, t);
@@ -1083,11 +1102,11 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
       } else if (due && g.gl == 0) {
         SFL_NU
         for (;;) {                                                        // agent_iter: FIFO in train-handle order
-          if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<TRACE>(e, hp, env_id);
+          if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<KIND>(e, hp, env_id);
           if (h->terminated || h->truncated || !h->active_mask) break;
           int t = ffs64(h->active_mask);
           h->active_mask &= h->active_mask - 1;
-          decide<TRACE>(e, hp, env_id, t);
+          decide<KIND>(e, hp, env_id, t);
         }
         if (h->terminated || h->truncated) episode_end(e, env_id);
       }
@@ -1102,7 +1121,7 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
       if (on) { need_reset = 0; R.elapsed = 0; R.ended = 0; R.rng_blk = -1; R.active = 0; R.done = 0; R.malf_prev = 0; }
       any_reset = 0;
     }
-    env_tick<G, TRACE>(e, sc, hp, env_id, g, R, live && !paused);
+    env_tick<G, KIND>(e, sc, hp, env_id, g, R, live && !paused);
   }
   g.sync();
   if (valid && g.gl == 0) {
