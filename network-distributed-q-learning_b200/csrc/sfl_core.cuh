@@ -198,24 +198,30 @@ template <bool TH, bool SQ_ = false> struct EnvT {
 
 
 
-// per-group exchange area of one tick (shared memory on the device), sized by T
+// per-group exchange area of one tick (shared memory on the device), sized by T; one 32-bit base, layout
+// [tmp 16T | rng 16T | occ T | blk T]:
+//   tmp  {src, dst, expected cell, new heading | preprocessed action<<8 | popped action<<16 | flags<<24}
+//   rng  the 16 stage-1 malfunction bytes of the current 16-tick block (one Philox call per train and block);
+//        replay injects recorded events instead of drawing, so `inj` (durations injected this tick) aliases it
+//   occ  train standing on my destination cell, or -1;   blk  movement blocked
 struct Scratch {
-  int4 *tmp;               // [T] {src, dst, expected cell, new heading | preprocessed action<<8 | popped action<<16 | flags<<24}
-  int8_t *occ;             // [T] train standing on my destination cell, or -1
-  uint8_t *blk;            // [T] movement blocked
-  int *inj;                // [T] replay only: injected malfunction durations of this tick
-  int4 *rng;               // [T] the 16 stage-1 malfunction bytes of the current 16-tick block (one Philox call per train and block)
+  hot_t base;
+  SFL_FN int4 *tmp() const { return (int4 *)hot_ptr(base); }
+  SFL_FN int4 *rng() const { return (int4 *)(hot_ptr(base) + 16 * c_L.T); }
+  SFL_FN int *inj() const { return (int *)(hot_ptr(base) + 16 * c_L.T); }
+  SFL_FN int8_t *occ() const { return (int8_t *)(hot_ptr(base) + 32 * c_L.T); }
+  SFL_FN uint8_t *blk() const { return (uint8_t *)(hot_ptr(base) + 33 * c_L.T); }
 };
 #if SFL_DEV
 __host__
 #endif
 SFL_FN unsigned scratch_bytes(int T) { return (unsigned)(32 * T + ((2 * T + 15) / 16) * 16); }
-SFL_FN Scratch make_scratch(char *p, int T) {
-  Scratch s;
-  s.tmp = (int4 *)p; s.rng = (int4 *)(p + 16 * T); s.occ = (int8_t *)(p + 32 * T); s.blk = (uint8_t *)(p + 33 * T);
-  s.inj = (int *)s.rng;                        // replay injects recorded events instead of drawing: the areas never coexist
-  return s;
-}
+
+// the environment's hyper-parameters (staged next to the hot state on the device): a 32-bit handle, not a pointer
+struct Hp {
+  hot_t o;
+  SFL_FN const sfl_hparams *operator->() const { return (const sfl_hparams *)hot_ptr(o); }
+};
 
 // ------------------------------------------------------------------------------------------------ kernel kinds
 // The run mode is a compile-time property of the two production kernels (learn, greedy): with the mode a runtime
@@ -288,7 +294,7 @@ SFL_FN int port_blocked(Env e, int next_port, int out_port, int me, int now) {
 // exactly where the reference's __check_entry (distr_q.py:47-57) would insert a dict entry, so the exported
 // key set equals the reference's.
 template <class Env>
-SFL_NI double *q_row(Env e, const sfl_hparams *hp, unsigned key) {
+SFL_NI double *q_row(Env e, const Hp hp, unsigned key) {
   if (Env::SQ) return c_ra.sq_q + (size_t)key * c_L.a_max;              // shared-table mode: dense, initialised by the host
   unsigned mask = (unsigned)c_L.q_cap - 1u;
   unsigned i = (key * 2654435761u) >> 7;
@@ -340,7 +346,7 @@ SFL_FN double lr_pow(double rate, int n) {
 
 // distr_q.py:419-447 update (fp64, Python operator order, no FMA contraction)
 template <class Env>
-SFL_NI void q_update(Env e, const sfl_hparams *hp, unsigned key, int action, double reward,
+SFL_NI void q_update(Env e, const Hp hp, unsigned key, int action, double reward,
                      const double *next_row, int prev_sw, int next_sw) {
   double *row = q_row(e, hp, key);
   double lr = hp->lr;
@@ -446,7 +452,7 @@ SFL_FN int delay_at(Env e, int tgt_index, int cell, int dir, int now, int la) {
 // the tail of one iteration of distr_q.py:302-362 that must wait for the train ticks run inside env.step()
 // (switch_env.py:648-649): arrival flush (:345-356), interaction counter (:362), truncation (switch_env.py:652-657)
 template <int KIND, class Env>
-SFL_FN void finish_decision(Env e, const sfl_hparams *hp, int env_id) {
+SFL_FN void finish_decision(Env e, const Hp hp, int env_id) {
   const bool TRACE = KIND == K_FULL;
   const int mode = run_mode<KIND>();
   EnvHdr *h = e.h();
@@ -524,7 +530,7 @@ SFL_FN Obs observe(Env e, int t, int now, const int4 ta, const int4 tb) {
 
 // one switch-agent decision: observe (O1-O3) -> act (Q1) -> apply (E2, E3, R1) -> Q-update (Q2, Q3)
 template <int KIND, class Env>
-SFL_FN void decide(Env e, const sfl_hparams *hp, int env_id, int t) {
+SFL_FN void decide(Env e, const Hp hp, int env_id, int t) {
   const bool TRACE = KIND == K_FULL;
   const int mode = run_mode<KIND>();
   EnvHdr *h = e.h();
@@ -720,7 +726,7 @@ struct TickRegs {
 //   stage 2  candidates only: Philox counter (tick, train, 0xA11E, 0); event iff word 0 < thr2 = floor(thr * 256 / B)
 //            (sfl_hparams.malf_thr2; probability thr2 / 2^32, product = thr / 2^32); word 1 gives the duration
 //            min + U{0..max-min} + 1.
-SFL_FN int malf_stage2(const sfl_hparams *hp, int now, int t) {
+SFL_FN int malf_stage2(const Hp hp, int now, int t) {
   const U4 u = philox4x32((unsigned)now, (unsigned)t, 0xA11Eu, 0u, (unsigned)hp->seed, (unsigned)(hp->seed >> 32));
   if (u.x >= hp->malf_thr2) return 0;
   return hp->malf_min + (int)(((unsigned long long)u.y * (unsigned)(hp->malf_max - hp->malf_min + 1)) >> 32) + 1;
@@ -729,7 +735,7 @@ SFL_FN int malf_stage2(const sfl_hparams *hp, int now, int t) {
 template <int G, int KIND, class Env>
 // `live` = this group's environment takes part (not halted, not an idle slot of the last warp); every loop bound and
 // branch that contains a collective is warp-uniform, the per-group work inside is predicated.
-SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const Grp<G> &g, TickRegs &R, const int live) {
+SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g, TickRegs &R, const int live) {
   const bool TRACE = KIND == K_FULL;
   EnvHdr *h = e.h();
   const int Tw = c_L.T;                                                  // warp-uniform loop bound
@@ -739,13 +745,13 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
   const unsigned thr = live ? hp->malf_threshold : 0u;
   if (replay_ev) {
     SFL_NU
-    for (int t = g.gl; t < T; t += G) sc.inj[t] = 0;
+    for (int t = g.gl; t < T; t += G) sc.inj()[t] = 0;
     g.sync();
     if (live && g.gl == 0) {
       const int *ev = c_ra.replay_ev + (size_t)env_id * c_ra.ev_cap * 3;
       int c = h->ev_cursor;
       SFL_NU
-      while (c < c_ra.ev_cap && ev[c * 3] >= 0 && ev[c * 3] <= now) { if (ev[c * 3] == now) sc.inj[ev[c * 3 + 1]] = ev[c * 3 + 2]; c++; }
+      while (c < c_ra.ev_cap && ev[c * 3] >= 0 && ev[c * 3] <= now) { if (ev[c * 3] == now) sc.inj()[ev[c * 3 + 1]] = ev[c * 3 + 2]; c++; }
       h->ev_cursor = c;
     }
     g.sync();
@@ -762,13 +768,13 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
     int pl = ta.z >> 16, mc = ta.w & 0xFFFF;
     // F5 malfunction draw: every train, every tick; applied only when the counter is 0
     int dur = 0;
-    if (replay_ev) dur = sc.inj[t];
+    if (replay_ev) dur = sc.inj()[t];
     else if (thr) {
       if (fresh_rng) {
         U4 u = philox4x32((unsigned)(now >> 4), (unsigned)t, 0xA11Fu, 0u, (unsigned)hp->seed, (unsigned)(hp->seed >> 32));
-        sc.rng[t] = make_int4((int)u.x, (int)u.y, (int)u.z, (int)u.w);
+        sc.rng()[t] = make_int4((int)u.x, (int)u.y, (int)u.z, (int)u.w);
       }
-      if (((const uint8_t *)&sc.rng[t])[now & 15] < coarse) dur = malf_stage2(hp, now, t);
+      if (((const uint8_t *)&sc.rng()[t])[now & 15] < coarse) dur = malf_stage2(hp, now, t);
     }
     if (mc == 0 && dur > 0) mc = dur;
     int src, dst, ecell = -1, nd = d, act = A_NOTHING, a = A_NOTHING, flags = 0;
@@ -797,7 +803,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
     ta.z = (int)plan | (pl << 16);
     ta.w = (ta.w & (int)0xFFFF0000) | mc;
     e.tra()[t] = ta;
-    sc.tmp[t] = make_int4(src, dst, ecell, nd | (act << 8) | (a << 16) | (flags << 24));
+    sc.tmp()[t] = make_int4(src, dst, ecell, nd | (act << 8) | (a << 16) | (flags << 24));
   }
   if (fresh_rng) R.rng_blk = now >> 4;
   g.sync();
@@ -808,19 +814,19 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
     const int t = base + g.gl;
     int follows = 0;
     if (t < T) {
-      int4 m = sc.tmp[t];
+      int4 m = sc.tmp()[t];
       int s = m.x, d = m.y;
       int wants = d != s, blocked = !wants, occ = -1;
       if (wants) {
         SFL_NU
         for (int k = 0; k < T; k++) {
-          const int2 o = *(const int2 *)&sc.tmp[k];
+          const int2 o = *(const int2 *)&sc.tmp()[k];
           occ = o.x == d ? k : occ;                                      // k != t: my own src differs from my dst
           blocked |= (o.y == d) & (o.y != o.x) & (k < t);                // lowest handle wins a contended cell
         }
-        if (occ >= 0) { int2 o = *(const int2 *)&sc.tmp[occ]; if (o.y == s && o.y != o.x) blocked = 1; }   // swap
+        if (occ >= 0) { int2 o = *(const int2 *)&sc.tmp()[occ]; if (o.y == s && o.y != o.x) blocked = 1; }   // swap
       }
-      sc.occ[t] = (int8_t)occ; sc.blk[t] = (uint8_t)blocked;
+      sc.occ()[t] = (int8_t)occ; sc.blk()[t] = (uint8_t)blocked;
       follows = !blocked && occ >= 0;
     }
     chain |= (unsigned long long)g.ballot(follows) << base;
@@ -833,8 +839,8 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
       if (chain) {
         SFL_NU
         for (int t = g.gl; t < T; t += G) {
-          int occ = sc.occ[t];
-          if (!sc.blk[t] && occ >= 0 && ((volatile uint8_t *)sc.blk)[occ]) { sc.blk[t] = 1; changed = 1; }
+          int occ = sc.occ()[t];
+          if (!sc.blk()[t] && occ >= 0 && ((volatile uint8_t *)sc.blk())[occ]) { sc.blk()[t] = 1; changed = 1; }
         }
       }
       g.sync();
@@ -850,7 +856,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
     int f_done = 0, f_malf = 0, f_stop = 0, f_dep = 0, f_act = 0;
     if (t < T) {
       int4 ta = e.tra()[t];
-      const int4 m = sc.tmp[t];
+      const int4 m = sc.tmp()[t];
       int p = ta.x, d = ta.y & 0xFF;
       const int st = (ta.y >> 8) & 0xFF;
       int saved = (ta.y >> 16) & 0xFF;
@@ -859,7 +865,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const sfl_hparams *hp, int env_id, const
       int pl = ta.z >> 16, mc = ta.w & 0xFFFF, next_port = (int)((unsigned)ta.w >> 16);
       const int act = (m.w >> 8) & 0xFF, popped = (m.w >> 16) & 0xFF, fl = (m.w >> 24) & 0xFF;
       const int wants = m.y != m.x;
-      const int in_malf = mc > 0, allowed = !in_malf && wants && !sc.blk[t];
+      const int in_malf = mc > 0, allowed = !in_malf && wants && !sc.blk()[t];
       const int4 tr0 = c_m.train0[t];
       const int ed = c_m.train1[t].x;
       const int ed_reached = now >= ed, stop_given = act == A_STOP, valid_move = is_moving(act) && allowed, conflict = !allowed;
@@ -1043,7 +1049,7 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
   char *gbase = c_ra.state + (size_t)env_id * c_L.env_stride;
   const unsigned hot_bytes = valid ? c_ra.hot_bytes : 0u;
   EnvT<TH, SQ> e;
-  const sfl_hparams *hp;
+  Hp hp;
   Scratch sc;
   e.gb = gbase;
 #if SFL_DEV
@@ -1058,14 +1064,14 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
     }
     g.sync();
     e.hot = stage;
-    hp = (const sfl_hparams *)(smem + c_ra.hot_bytes);
-    sc = make_scratch(smem + c_ra.hot_bytes + (unsigned)sizeof(sfl_hparams), c_L.T);
+    hp.o = stage + c_ra.hot_bytes;
+    sc.base = stage + c_ra.hot_bytes + (unsigned)sizeof(sfl_hparams);
   }
 #else
   (void)stage;
   e.hot = gbase;
-  hp = c_ra.hp + env_id;
-  sc = make_scratch(host_scratch, c_L.T);
+  hp.o = (char *)(c_ra.hp + env_id);
+  sc.base = host_scratch;
 #endif
   EnvHdr *h = e.h();
   TickRegs R;
