@@ -512,7 +512,7 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   Ctx *c = (Ctx *)ctx;
   if (!c) return fail(SFL_E_ARG, "null ctx%s");
   if (!c->bound) return fail(SFL_E_STATE, "sfl_bind first%s");
-  if (mode < SFL_MODE_LEARN || mode > SFL_MODE_STEP || max_ticks < 0) return fail(SFL_E_ARG, "bad mode / max_ticks%s");
+  if (mode < SFL_MODE_LEARN || mode > SFL_MODE_STEP || max_ticks < 0 || max_ticks > (1 << 25)) return fail(SFL_E_ARG, "bad mode / max_ticks (at most 2^25 ticks per launch)%s");
   if ((mode == SFL_MODE_REPLAY || mode == SFL_MODE_STEP) && (!c->bufs.replay_act || c->cfg.act_cap < 1))
     return fail(SFL_E_ARG, "replay / step mode needs replay_act (act_cap >= 1)%s");
   if (mode == SFL_MODE_STEP && !c->bufs.step_out) return fail(SFL_E_ARG, "step mode needs step_out%s");

@@ -715,8 +715,8 @@ SFL_FN void env_reset(Env e, const Grp<G> &g, int on) {
 // the header copy in shared memory is what the decision phase (first lane) reads and writes.
 struct TickRegs {
   int elapsed, ended, rng_blk;                 // rng_blk: 16-tick block the cached malfunction bytes belong to (-1: none)
-  unsigned long long active, done, malf_prev;
-  unsigned long long ticks, train_ticks;       // launch-local, added to the header at the end
+  unsigned long long active, done;
+  unsigned ticks, train_ticks;                 // launch-local (max_ticks * T < 2^32), added to the header at the end
 };
 
 // Malfunction draw of train t at tick `now` (row F5), probability thr / 2^32 = 1 - exp(-rate) per (train, tick), in two
@@ -981,15 +981,16 @@ SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g
   }
   if (live && g.gl == 0) {
     h->elapsed = now;
-    const unsigned long long new_malf = malf_bits & ~R.malf_prev;
+    const unsigned long long new_malf = malf_bits & ~h->malf_prev_mask;
     if (new_malf) h->num_malf += popc64(new_malf);                       // switch_env.py:399-401
+    if (malf_bits != h->malf_prev_mask) h->malf_prev_mask = malf_bits;
     if (done_bits != prev_done) h->done_mask = done_bits;
     if (ended) h->terminated = 1;
     if (active) h->active_mask = active;                                 // the queue is empty whenever a tick runs
     if (TRACE) { if (c_ra.trace_tick) h->n_tick_logged++; }
   }
-  R.elapsed = now; R.ended = ended; R.active = active; R.done = done_bits; R.malf_prev = malf_bits;
-  if (live) { R.ticks++; R.train_ticks += (unsigned long long)(T - popc64(prev_done)); }
+  R.elapsed = now; R.ended = ended; R.active = active; R.done = done_bits;
+  if (live) { R.ticks++; R.train_ticks += (unsigned)(T - popc64(prev_done)); }
   g.sync();
 }
 
@@ -1075,11 +1076,11 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
 #endif
   EnvHdr *h = e.h();
   TickRegs R;
-  R.elapsed = 0; R.ended = 0; R.rng_blk = -1; R.active = 0; R.done = 0; R.malf_prev = 0; R.ticks = 0; R.train_ticks = 0;
+  R.elapsed = 0; R.ended = 0; R.rng_blk = -1; R.active = 0; R.done = 0; R.ticks = 0; R.train_ticks = 0;
   int need_reset = 0, live = 0;
   if (valid) {
     R.elapsed = h->elapsed; R.ended = h->terminated | h->truncated;
-    R.active = h->active_mask; R.done = h->done_mask; R.malf_prev = h->malf_prev_mask;
+    R.active = h->active_mask; R.done = h->done_mask;
     need_reset = h->need_reset; live = !h->halted;
   }
   const int stepping = TRACE && run_mode<KIND>() == SFL_MODE_STEP;
@@ -1124,7 +1125,7 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
       if (live && need_reset && hp->episodes >= 0 && h->episode >= hp->episodes) live = 0;      // halt: need_reset stays set
       const int on = live && need_reset;
       env_reset<G>(e, g, on);
-      if (on) { need_reset = 0; R.elapsed = 0; R.ended = 0; R.rng_blk = -1; R.active = 0; R.done = 0; R.malf_prev = 0; }
+      if (on) { need_reset = 0; R.elapsed = 0; R.ended = 0; R.rng_blk = -1; R.active = 0; R.done = 0; }
       any_reset = 0;
     }
     env_tick<G, KIND>(e, sc, hp, env_id, g, R, live && !paused);
@@ -1132,7 +1133,6 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
   g.sync();
   if (valid && g.gl == 0) {
     h->halted = !live;
-    h->malf_prev_mask = R.malf_prev;
     h->ticks += R.ticks; h->train_ticks += R.train_ticks;
     sfl_env_counters *c = c_ra.counters + env_id;
     c->decisions = h->decisions; c->ticks = h->ticks; c->train_ticks = h->train_ticks; c->episodes = h->episode;
