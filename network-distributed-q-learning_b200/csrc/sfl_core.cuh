@@ -681,7 +681,7 @@ SFL_FN void decide(Env e, const Hp hp, int env_id, int t) {
 // switch_env.py:93-158 with a constant map: state re-init + the precomputed _init_ports table (:507-568)
 // (`on`: this group resets; the syncs are the whole warp's)
 template <int G, class Env>
-SFL_FN void env_reset(Env e, const Grp<G> &g, int on) {
+SFL_NI void env_reset(Env e, const Grp<G> &g, int on) {
   EnvHdr *h = e.h();
   const int T = on ? c_L.T : 0, NP = on ? c_L.NP : 0;
   SFL_NU
@@ -996,7 +996,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g
 
 // ------------------------------------------------------------------------------------------------ episode end
 template <class Env>
-SFL_FN void episode_end(Env e, int env_id) {   // first lane
+SFL_NI void episode_end(Env e, int env_id) {   // first lane
   EnvHdr *h = e.h();
   if (c_ra.ep_log && h->n_ep_logged < c_ra.ep_cap) {
     sfl_ep_rec *rec = c_ra.ep_log + (size_t)env_id * c_ra.ep_cap + h->n_ep_logged;
