@@ -96,11 +96,11 @@ __global__ void __launch_bounds__(SFL_CTA_THREADS) k_init(InitArgs ia) {
 // environment: [hot env state (hot_bytes) | sfl_hparams | Scratch]; the hot state (header, train records, pending
 // lists and -- when they fit -- semaphores, rewards and per-switch counters) is staged once per launch and written
 // back at the end, so the tick / decision loops touch HBM only for Q rows.
-template <int G, int KIND, bool TH, bool SQ>
+template <int G, int KIND, bool TH, bool SQ, bool ONE>
 __global__ void __launch_bounds__(SFL_CTA_THREADS, TH ? (G == 32 ? 7 : 4) : SFL_MINB_BIG) k_run() {
   const int slot = threadIdx.x / G;                    // environment slot inside the CTA
   const int env_id = blockIdx.x * (blockDim.x / G) + slot;
-  env_run<G, KIND, TH, SQ>(env_id, (unsigned)slot * c_ra.env_smem, nullptr);
+  env_run<G, KIND, TH, SQ, ONE>(env_id, (unsigned)slot * c_ra.env_smem, nullptr);
 }
 
 __global__ void k_sum(const sfl_env_counters *c, int n, unsigned long long *out) {
@@ -155,23 +155,25 @@ __global__ void __launch_bounds__(512) k_distance_map(const uint16_t *grid, int 
 }
 
 typedef void (*run_kernel_t)();
-template <int G> static run_kernel_t pick_kernel_g(int kind, int th, int sq) {
+// `one`: every train has its own lane (T <= G).  Only the small-map production kernels get that variant (it is where
+// T is small); everything else runs the general chunked loops.
+template <int G> static run_kernel_t pick_kernel_g(int kind, int th, int sq, int one) {
   if (sq) {                                                                              // shared-table variants: learn / greedy only
-    if (kind == K_GREEDY) return th ? k_run<G, K_GREEDY, true, true> : k_run<G, K_GREEDY, false, true>;
-    return th ? k_run<G, K_LEARN, true, true> : k_run<G, K_LEARN, false, true>;
+    if (kind == K_GREEDY) return th ? k_run<G, K_GREEDY, true, true, false> : k_run<G, K_GREEDY, false, true, false>;
+    return th ? k_run<G, K_LEARN, true, true, false> : k_run<G, K_LEARN, false, true, false>;
   }
-  if (kind == K_FULL) return th ? k_run<G, K_FULL, true, false> : k_run<G, K_FULL, false, false>;
-  if (kind == K_GREEDY) return th ? k_run<G, K_GREEDY, true, false> : k_run<G, K_GREEDY, false, false>;
-  return th ? k_run<G, K_LEARN, true, false> : k_run<G, K_LEARN, false, false>;
+  if (kind == K_FULL) return th ? k_run<G, K_FULL, true, false, false> : k_run<G, K_FULL, false, false, false>;
+  if (kind == K_GREEDY) return th ? (one ? k_run<G, K_GREEDY, true, false, true> : k_run<G, K_GREEDY, true, false, false>) : k_run<G, K_GREEDY, false, false, false>;
+  return th ? (one ? k_run<G, K_LEARN, true, false, true> : k_run<G, K_LEARN, true, false, false>) : k_run<G, K_LEARN, false, false, false>;
 }
-static run_kernel_t pick_kernel(int G, int kind, int th, int sq) {
+static run_kernel_t pick_kernel(int G, int kind, int th, int sq, int one) {
   switch (G) {
-    case 1: return pick_kernel_g<1>(kind, th, sq);
-    case 2: return pick_kernel_g<2>(kind, th, sq);
-    case 4: return pick_kernel_g<4>(kind, th, sq);
-    case 8: return pick_kernel_g<8>(kind, th, sq);
-    case 16: return pick_kernel_g<16>(kind, th, sq);
-    default: return pick_kernel_g<32>(kind, th, sq);
+    case 1: return pick_kernel_g<1>(kind, th, sq, one);
+    case 2: return pick_kernel_g<2>(kind, th, sq, one);
+    case 4: return pick_kernel_g<4>(kind, th, sq, one);
+    case 8: return pick_kernel_g<8>(kind, th, sq, one);
+    case 16: return pick_kernel_g<16>(kind, th, sq, one);
+    default: return pick_kernel_g<32>(kind, th, sq, one);
   }
 }
 #endif
@@ -545,7 +547,7 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   if (smem > 227u * 1024u) return fail(SFL_E_ARG, "environment state does not fit shared memory with this many lanes per env: use more lanes%s");
   int grid = (c->cfg.n_envs + envs_per_cta - 1) / envs_per_cta;
   if (c->cfg.shared_q && trace) return fail(SFL_E_ARG, "shared-table mode has no trace / step variants%s");
-  run_kernel_t k = pick_kernel(G, kind, (int)c->tail_hot, c->cfg.shared_q);
+  run_kernel_t k = pick_kernel(G, kind, (int)c->tail_hot, c->cfg.shared_q, c->L.T <= G);
   CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(set_constants(c, &ra, stream));
   k<<<grid, threads, smem, (cudaStream_t)stream>>>();
@@ -556,10 +558,10 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   for (int i = 0; i < c->cfg.n_envs; i++) {
     if (c->cfg.shared_q) {
       if (trace) return fail(SFL_E_ARG, "shared-table mode has no trace / step variants%s");
-      if (kind == K_GREEDY) env_run<1, K_GREEDY, true, true>(i, 0u, host_scratch); else env_run<1, K_LEARN, true, true>(i, 0u, host_scratch);
-    } else if (kind == K_FULL) env_run<1, K_FULL, true, false>(i, 0u, host_scratch);
-    else if (kind == K_GREEDY) env_run<1, K_GREEDY, true, false>(i, 0u, host_scratch);
-    else env_run<1, K_LEARN, true, false>(i, 0u, host_scratch);
+      if (kind == K_GREEDY) env_run<1, K_GREEDY, true, true, false>(i, 0u, host_scratch); else env_run<1, K_LEARN, true, true, false>(i, 0u, host_scratch);
+    } else if (kind == K_FULL) env_run<1, K_FULL, true, false, false>(i, 0u, host_scratch);
+    else if (kind == K_GREEDY) env_run<1, K_GREEDY, true, false, false>(i, 0u, host_scratch);
+    else env_run<1, K_LEARN, true, false, false>(i, 0u, host_scratch);
   }
 #endif
   return SFL_OK;

@@ -302,3 +302,41 @@ def test_cuda_distance_map_large_grid_uses_the_global_memory_variant():
     d = backend.device_distance_map(fx["grid"], cells)
     for k, (r, c) in enumerate(fx["target"]):
         assert np.array_equal(d[k], railmap.distance_to(fx["grid"], (int(r), int(c)))), k
+
+
+@pytest.mark.parametrize("name,lanes", [("c1_synth18", None), ("c1_synth18", 1), ("slips24_t6", None), ("slips24_t6", 4),
+                                        ("synth40_t12", 8), ("c4_synth100_t50", None)])
+def test_cuda_production_kernels_equal_the_full_kernel(name, lanes):
+    """The learn / greedy kernels are compile-time specialisations (no trace, no replay, single-pass train loops when
+    T <= lanes).  Free-running learn and a greedy rollout through them must give exactly what the full kernel -- the one
+    the replay tests pin against the reference -- gives for the same seeds: counters, episode logs, Q-tables."""
+    fx, _ = load_golden(name)
+    rm = backend.RailMap(fx)
+    hp = dict(gamma=0.95, epsilon=0.5, epsilon_decay_rate=0.999, lr=0.2, lr_decay_rate=0.9999, default_q=1.0)
+    B, n_ep = 6, 3
+
+    def run(full):
+        eng = gpu_engine(rm, n_envs=B, q_cap=32768 if "c4" in name else 4096, ep_cap=8, lanes=lanes,
+                         dec_cap=4 if full else 0, tick_cap=0)
+        eng.set_hparams(**hp, seeds=np.arange(B) + 77, episodes=n_ep)
+        eng.reset()
+        eng.enable_q_init(True)
+        eng.run(backend.MODE_LEARN, 1_000_000)
+        eng.check_errors(allow=backend.ERR_NO_TRAIN_AT_SWITCH)
+        c1 = eng.counters().copy()
+        _, log1, d1 = eng.episode_log()
+        eng.set_hparams(**hp, seeds=np.arange(B) + 77, episodes=1, episode_base=n_ep)
+        eng.reset(keep_q=True, keep_interactions=True)
+        eng.run(backend.MODE_GREEDY, 1_000_000)
+        eng.check_errors(allow=backend.ERR_NO_TRAIN_AT_SWITCH)
+        c2 = eng.counters().copy()
+        _, log2, d2 = eng.episode_log()
+        q = [eng.export_q(i) for i in range(B)]
+        eng.close()
+        return c1, log1[:, :n_ep].copy(), d1[:, :n_ep].copy(), c2, log2[:, :1].copy(), d2[:, :1].copy(), q
+
+    a, b = run(full=True), run(full=False)
+    for k in ("decisions", "ticks", "train_ticks", "episodes", "err", "q_rows", "aborted"):
+        assert np.array_equal(a[0][k], b[0][k]) and np.array_equal(a[3][k], b[3][k]), k
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
+    assert a[6] == b[6]
