@@ -155,16 +155,18 @@ __global__ void __launch_bounds__(512) k_distance_map(const uint16_t *grid, int 
 }
 
 typedef void (*run_kernel_t)();
-// `one`: every train has its own lane (T <= G).  Only the small-map production kernels get that variant (it is where
-// T is small); everything else runs the general chunked loops.
+// `one`: every train has its own lane (T <= G): the production kernels have a single-pass variant for that; the full and
+// the shared-table kernels always run the general chunked loops.
 template <int G> static run_kernel_t pick_kernel_g(int kind, int th, int sq, int one) {
   if (sq) {                                                                              // shared-table variants: learn / greedy only
     if (kind == K_GREEDY) return th ? k_run<G, K_GREEDY, true, true, false> : k_run<G, K_GREEDY, false, true, false>;
     return th ? k_run<G, K_LEARN, true, true, false> : k_run<G, K_LEARN, false, true, false>;
   }
   if (kind == K_FULL) return th ? k_run<G, K_FULL, true, false, false> : k_run<G, K_FULL, false, false, false>;
-  if (kind == K_GREEDY) return th ? (one ? k_run<G, K_GREEDY, true, false, true> : k_run<G, K_GREEDY, true, false, false>) : k_run<G, K_GREEDY, false, false, false>;
-  return th ? (one ? k_run<G, K_LEARN, true, false, true> : k_run<G, K_LEARN, true, false, false>) : k_run<G, K_LEARN, false, false, false>;
+  if (kind == K_GREEDY) return th ? (one ? k_run<G, K_GREEDY, true, false, true> : k_run<G, K_GREEDY, true, false, false>)
+                                  : (one ? k_run<G, K_GREEDY, false, false, true> : k_run<G, K_GREEDY, false, false, false>);
+  return th ? (one ? k_run<G, K_LEARN, true, false, true> : k_run<G, K_LEARN, true, false, false>)
+            : (one ? k_run<G, K_LEARN, false, false, true> : k_run<G, K_LEARN, false, false, false>);
 }
 static run_kernel_t pick_kernel(int G, int kind, int th, int sq, int one) {
   switch (G) {
