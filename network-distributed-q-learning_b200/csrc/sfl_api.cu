@@ -202,7 +202,7 @@ static int choose_hot(Ctx *c) {
   const unsigned per_warp = 32u / (unsigned)c->lanes;
   if ((size_t)(c->L.off_q + fixed) * per_warp <= 14u * 1024u) { c->tail_hot = 1; c->hot_bytes = c->L.off_q; }   // >= 16 warps per SM
   else { c->tail_hot = 0; c->hot_bytes = c->L.off_pend; }
-  c->env_smem = c->hot_bytes + fixed;
+  c->env_smem = c->hot_bytes + fixed + (c->tail_hot ? 0u : ((unsigned)c->L.NP + 15u) / 16u * 16u);   // + holder bytes of the semaphores
   return (size_t)c->env_smem * per_warp > 227u * 1024u;
 }
 

@@ -183,6 +183,7 @@ SFL_FN char *hot_ptr(hot_t o) { return o; }
 // Q-row functions cost the private-table kernels 20-25 % on large maps (registers / code size at 72 registers)
 template <bool TH, bool SQ_ = false> struct EnvT {
   static const bool SQ = SQ_;
+  static const bool HOT_TAIL = TH;
   hot_t hot;               // staged copy of the first hot_bytes of the env block (the env block itself on the host build)
   char *gb;                // the env block in HBM
   SFL_FN EnvHdr *h() const { return (EnvHdr *)hot_ptr(hot); }
@@ -194,6 +195,14 @@ template <bool TH, bool SQ_ = false> struct EnvT {
   SFL_FN int *rewards() const { return (int *)(tail() + c_L.off_rewards); }
   SFL_FN SwS *sws() const { return (SwS *)(tail() + c_L.off_sws); }
   SFL_FN double *q() const { return (double *)(gb + c_L.off_q); }
+  // Who holds the record of port p (-1: nobody).  When the semaphore table stays in HBM (large maps) a byte mirror of
+  // the holders lives in shared memory: "is there a record / is it mine / is its holder stopped" -- most of what the
+  // decision and the per-tick semaphore phases ask -- is then answered without touching global memory.
+  hot_t own;
+  SFL_FN uint8_t *own_ptr() const { return (uint8_t *)hot_ptr(own); }
+  SFL_FN int owner(int p) const { return TH ? sem()[p].z : (int)(int8_t)own_ptr()[p]; }
+  SFL_FN void sem_put(int p, int4 r) const { sem()[p] = r; if (!TH) own_ptr()[p] = (uint8_t)r.z; }
+  SFL_FN void sem_drop(int p) const { sem()[p].z = -1; if (!TH) own_ptr()[p] = 0xFFu; }
 };
 
 
@@ -275,8 +284,16 @@ template <class Env>
 SFL_FN int tr_state(Env e, int t) { return (e.tra()[t].y >> 8) & 0xFF; }
 template <class Env>
 SFL_FN int rule_port(Env e, int port, int me, int now, int blocking_type) {
-  int4 r = e.sem()[port];
-  if (r.z < 0 || r.z == me || r.x > now || r.y < now) return 0;
+  int4 r;
+  if (Env::HOT_TAIL) {                                                        // staged table: one shared-memory load
+    r = e.sem()[port];
+    if (r.z < 0 || r.z == me || r.x > now || r.y < now) return 0;
+  } else {                                                              // table in HBM: ask the holder mirror first
+    const int holder = e.owner(port);
+    if (holder < 0 || holder == me) return 0;
+    r = e.sem()[port];
+    if (r.x > now || r.y < now) return 0;
+  }
   if (r.w == blocking_type) return 1;
   return tr_state(e, r.z) == ST_MALF;
 }
@@ -402,7 +419,7 @@ SFL_FN void sem_delete_owned(Env e, int port, int h) {
   SFL_NU
   for (int k = 0; k < sw.x; k++) {
     int p = sw.z + k;
-    if (e.sem()[p].z == h) e.sem()[p].z = -1;
+    if (e.owner(p) == h) e.sem_drop(p);
   }
 }
 
@@ -413,31 +430,59 @@ SFL_FN void transition_semaphore(Env e, int source, int out_port, int target, in
     sem_delete_owned(e, old_next, h);
     if (old_prev >= 0) sem_delete_owned(e, old_prev, h);
   }
-  int4 r = e.sem()[out_port];                                           // :326-334
-  if (r.z < 0) e.sem()[out_port] = make_int4(now, now + 3, h, SEM_OUT);
-  else if (r.w == SEM_OUT || r.x > now) e.sem()[out_port] = make_int4(now, now + 3, h, r.w);
-  int d_ot = c_m.port[out_port].y;
-  r = e.sem()[target];                                                  // :336-344
-  if (r.z < 0) e.sem()[target] = make_int4(now, now + d_ot + 1, h, SEM_IN);
-  else if (r.w == SEM_IN || r.x > now) e.sem()[target] = make_int4(now, now + d_ot + 1, h, r.w);
-  int unique = c_m.port[target].z;
-  if (unique >= 0) {                                                    // :356 forced path through the next switch
-    int4 up = c_m.port[unique];
-    int far_port = up.x;
-    if (unique != source && unique != out_port && unique != target) {   // :368-378
-      r = e.sem()[unique];
-      if (r.z < 0 || r.w == SEM_OUT || r.x > now) e.sem()[unique] = make_int4(now, now + d_ot + 1, h, SEM_OUT);
+  if (Env::HOT_TAIL) {                                                        // staged table: load, test, store
+    int4 r = e.sem()[out_port];                                           // :326-334
+    if (r.z < 0) e.sem()[out_port] = make_int4(now, now + 3, h, SEM_OUT);
+    else if (r.w == SEM_OUT || r.x > now) e.sem()[out_port] = make_int4(now, now + 3, h, r.w);
+    int d_ot = c_m.port[out_port].y;
+    r = e.sem()[target];                                                  // :336-344
+    if (r.z < 0) e.sem()[target] = make_int4(now, now + d_ot + 1, h, SEM_IN);
+    else if (r.w == SEM_IN || r.x > now) e.sem()[target] = make_int4(now, now + d_ot + 1, h, r.w);
+    int unique = c_m.port[target].z;
+    if (unique >= 0) {                                                    // :356 forced path through the next switch
+      int4 up = c_m.port[unique];
+      int far_port = up.x;
+      if (unique != source && unique != out_port && unique != target) {   // :368-378
+        r = e.sem()[unique];
+        if (r.z < 0 || r.w == SEM_OUT || r.x > now) e.sem()[unique] = make_int4(now, now + d_ot + 1, h, SEM_OUT);
+      }
+      r = e.sem()[unique];                                                // :380-388 (the list == 'out' test is never true)
+      if (r.z < 0 || r.x > now) e.sem()[unique] = make_int4(now, now + d_ot, h, SEM_OUT);
+      if (far_port != source && far_port != out_port && far_port != unique) {   // :390-402
+        r = e.sem()[far_port];
+        if (r.z < 0 || r.w == SEM_IN || r.x > now) e.sem()[far_port] = make_int4(now, now + d_ot + up.y + 1, h, SEM_IN);
+      }
     }
-    r = e.sem()[unique];                                                // :380-388 (the list == 'out' test is never true)
-    if (r.z < 0 || r.x > now) e.sem()[unique] = make_int4(now, now + d_ot, h, SEM_OUT);
-    if (far_port != source && far_port != out_port && far_port != unique) {   // :390-402
-      r = e.sem()[far_port];
-      if (r.z < 0 || r.w == SEM_IN || r.x > now) e.sem()[far_port] = make_int4(now, now + d_ot + up.y + 1, h, SEM_IN);
+    if (target != source && target != out_port) {                         // :404-414 moving edge
+      r = e.sem()[target];
+      if (r.z < 0 || r.w == SEM_OUT || r.x > now) e.sem()[target] = make_int4(now, now + d_ot + 1, h, SEM_OUT);
     }
-  }
-  if (target != source && target != out_port) {                         // :404-414 moving edge
-    r = e.sem()[target];
-    if (r.z < 0 || r.w == SEM_OUT || r.x > now) e.sem()[target] = make_int4(now, now + d_ot + 1, h, SEM_OUT);
+  } else {                                                              // table in HBM: the holder mirror answers "nobody" without a load
+    int4 r;                                                             // :326-334
+    if (e.owner(out_port) < 0) e.sem_put(out_port, make_int4(now, now + 3, h, SEM_OUT));
+    else { r = e.sem()[out_port]; if (r.w == SEM_OUT || r.x > now) e.sem_put(out_port, make_int4(now, now + 3, h, r.w)); }
+    int d_ot = c_m.port[out_port].y;
+    if (e.owner(target) < 0) e.sem_put(target, make_int4(now, now + d_ot + 1, h, SEM_IN));            // :336-344
+    else { r = e.sem()[target]; if (r.w == SEM_IN || r.x > now) e.sem_put(target, make_int4(now, now + d_ot + 1, h, r.w)); }
+    int unique = c_m.port[target].z;
+    if (unique >= 0) {                                                  // :356 forced path through the next switch
+      int4 up = c_m.port[unique];
+      int far_port = up.x;
+      if (unique != source && unique != out_port && unique != target) { // :368-378
+        r = e.sem()[unique];
+        if (e.owner(unique) < 0 || r.w == SEM_OUT || r.x > now) e.sem_put(unique, make_int4(now, now + d_ot + 1, h, SEM_OUT));
+      }
+      r = e.sem()[unique];                                              // :380-388 (the list == 'out' test is never true)
+      if (e.owner(unique) < 0 || r.x > now) e.sem_put(unique, make_int4(now, now + d_ot, h, SEM_OUT));
+      if (far_port != source && far_port != out_port && far_port != unique) {   // :390-402
+        r = e.sem()[far_port];
+        if (e.owner(far_port) < 0 || r.w == SEM_IN || r.x > now) e.sem_put(far_port, make_int4(now, now + d_ot + up.y + 1, h, SEM_IN));
+      }
+    }
+    if (target != source && target != out_port) {                       // :404-414 moving edge
+      r = e.sem()[target];
+      if (e.owner(target) < 0 || r.w == SEM_OUT || r.x > now) e.sem_put(target, make_int4(now, now + d_ot + 1, h, SEM_OUT));
+    }
   }
 }
 
@@ -693,7 +738,7 @@ SFL_NI void env_reset(Env e, const Grp<G> &g, int on) {
     e.trb()[t] = make_int4(b.x, 0xFFFF, c_m.init_delay[t], 0);
   }
   SFL_NU
-  for (int p = g.gl; p < NP; p += G) e.sem()[p] = make_int4(0, 0, -1, 0);
+  for (int p = g.gl; p < NP; p += G) e.sem_put(p, make_int4(0, 0, -1, 0));
   SFL_NU
   for (int i = g.gl; i < c_L.S * T; i += G) e.rewards()[i] = 0;
   g.sync();
@@ -701,7 +746,7 @@ SFL_NI void env_reset(Env e, const Grp<G> &g, int on) {
     SFL_NU
     for (int t = 0; t < T; t++) {                                         // switch_env.py:564-568, train order
       int4 tr1 = c_m.train1[t];
-      e.sem()[tr1.z] = make_int4(tr1.x - 2, tr1.x + tr1.w, t, SEM_IN);
+      e.sem_put(tr1.z, make_int4(tr1.x - 2, tr1.x + tr1.w, t, SEM_IN));
     }
     h->elapsed = 0; h->step_counter = 0; h->num_malf = 0; h->terminated = 0; h->truncated = 0; h->need_reset = 0;
     h->pending_fin = -1; h->cur_dec = -1; h->ev_cursor = 0; h->active_mask = 0; h->malf_prev_mask = 0; h->at_dest_mask = 0;
@@ -941,8 +986,8 @@ SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g
     const int NP = release ? c_L.NP : 0;
     SFL_NU
     for (int p = g.gl; p < NP; p += G) {
-      int tr = e.sem()[p].z;
-      if (tr >= 0 && (ended || ((done_bits >> tr) & 1))) e.sem()[p].z = -1;
+      int tr = e.owner(p);
+      if (tr >= 0 && (ended || ((done_bits >> tr) & 1))) e.sem_drop(p);
     }
   }
   // ---- phase D3: departure bookings (switch_env.py:379-384), train order
@@ -954,7 +999,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g
       while (b) {
         int t = ffs64(b); b &= b - 1;
         int4 tr1 = c_m.train1[t];
-        e.sem()[(unsigned)e.tra()[t].w >> 16] = make_int4(tr1.x - 2, tr1.x + tr1.w, t, SEM_IN);
+        e.sem_put((int)((unsigned)e.tra()[t].w >> 16), make_int4(tr1.x - 2, tr1.x + tr1.w, t, SEM_IN));
       }
     }
   }
@@ -964,8 +1009,13 @@ SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g
     const int NP = stopped_bits ? c_L.NP : 0;
     SFL_NU
     for (int p = g.gl; p < NP; p += G) {
-      int4 r = e.sem()[p];
-      if (r.z >= 0 && ((stopped_bits >> r.z) & 1)) { r.y = now + (r.y - r.x); r.x = now; e.sem()[p] = r; }
+      if (Env::HOT_TAIL) {
+        int4 r = e.sem()[p];
+        if (r.z >= 0 && ((stopped_bits >> r.z) & 1)) { r.y = now + (r.y - r.x); r.x = now; e.sem()[p] = r; }
+      } else {
+        const int holder = e.owner(p);                                   // only the records of stopped trains leave shared memory
+        if (holder >= 0 && ((stopped_bits >> holder) & 1)) { int4 r = e.sem()[p]; r.y = now + (r.y - r.x); r.x = now; e.sem()[p] = r; }
+      }
     }
     g.sync();
     if (stopped_bits && g.gl == 0) {
@@ -976,7 +1026,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g
         int4 ta = e.tra()[t];
         if (((ta.y >> 8) & 0xFF) == ST_MALF) {
           int port = (int)((unsigned)ta.w >> 16);
-          if (e.sem()[port].z < 0) e.sem()[port] = make_int4(now, now + c_m.train1[t].w, t, SEM_IN);
+          if (e.owner(port) < 0) e.sem_put(port, make_int4(now, now + c_m.train1[t].w, t, SEM_IN));
         }
       }
     }
@@ -1069,10 +1119,18 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
     e.hot = stage;
     hp.o = stage + c_ra.hot_bytes;
     sc.base = stage + c_ra.hot_bytes + (unsigned)sizeof(sfl_hparams);
+    e.own = sc.base + scratch_bytes(c_L.T);
+    if (!TH) {                                                            // holders of the semaphore records, from HBM
+      const int NPv = valid ? c_L.NP : 0;
+      SFL_NU
+      for (int p = g.gl; p < NPv; p += G) e.own_ptr()[p] = (uint8_t)e.sem()[p].z;
+      g.sync();
+    }
   }
 #else
   (void)stage;
   e.hot = gbase;
+  e.own = gbase;                                                          // unused: the host build keeps everything "hot"
   hp.o = (char *)(c_ra.hp + env_id);
   sc.base = host_scratch;
 #endif
