@@ -81,7 +81,7 @@ SFL_FN void env_init(const InitArgs &ia, int env_id, int lane, int lanes) {
     int q_rows = ia.keep_q ? e.h()->q_rows : 0;
     EnvHdr z;
     memset(&z, 0, sizeof(z));
-    z.need_reset = 1; z.pending_fin = -1; z.cur_dec = -1; z.q_rows = q_rows; z.cur_train = -1; z.last_next_sw = -1;
+    z.need_reset = 1; z.pending_fin = -1; z.cur_dec = -1; z.q_rows = q_rows; z.cur_train = -1; z.last_next_sw = -1; z.eps_tag = -1;
     *e.h() = z;
   }
 }

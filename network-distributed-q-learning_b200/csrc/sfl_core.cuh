@@ -137,7 +137,9 @@ struct EnvHdr {            // 128 bytes at the start of every env block
   unsigned long long active_mask, malf_prev_mask, at_dest_mask, done_mask;
   unsigned long long decisions, ticks, train_ticks;
   double cum_reward;
-  int last_next_sw, pad2, pad3, pad4;  // last_next_sw: "next_switch" of the most recent decision (SFL_MODE_STEP)
+  int last_next_sw;                    // "next_switch" of the most recent decision (SFL_MODE_STEP)
+  int eps_tag;                         // epsilon-greedy draw cache: pair of decisions (step_counter >> 1) the words below belong to
+  unsigned eps_z, eps_w;               //   words 2 and 3 of that pair's Philox block (the odd decision of the pair uses them)
 };
 
 // Per-train records (16 bytes each, one vector load per phase):
@@ -615,10 +617,20 @@ SFL_FN void decide(Env e, const Hp hp, int env_id, int t) {
     }
   } else if (mode == SFL_MODE_LEARN) {
     double eps = dmul(hp->epsilon, e.sws()[s].eps_pow);
-    U4 u = philox4x32((unsigned)h->step_counter, (unsigned)(hp->episode_base + h->episode), 0x5F1u, 0u, (unsigned)hp->seed, (unsigned)(hp->seed >> 32));
-    double u01 = ((double)u.x + 0.5) * (1.0 / 4294967296.0);
+    // one Philox4x32-10 block per PAIR of decisions: counter (step_counter >> 1, episode, 0x5F1, 0), key = env seed; the
+    // even decision of the pair uses words 0-1, the odd one words 2-3 (kept in the header, so the stream does not depend
+    // on how the run is cut into launches)
+    const int pair = h->step_counter >> 1;
+    unsigned ux, uy;
+    if ((h->step_counter & 1) && h->eps_tag == pair) { ux = h->eps_z; uy = h->eps_w; }
+    else {
+      const U4 u = philox4x32((unsigned)pair, (unsigned)(hp->episode_base + h->episode), 0x5F1u, 0u, (unsigned)hp->seed, (unsigned)(hp->seed >> 32));
+      h->eps_tag = pair; h->eps_z = u.z; h->eps_w = u.w;
+      if (h->step_counter & 1) { ux = u.z; uy = u.w; } else { ux = u.x; uy = u.y; }
+    }
+    double u01 = ((double)ux + 0.5) * (1.0 / 4294967296.0);
     if (u01 < eps) {                                       // explore: uniform over the allowed actions
-      int pick = (int)(((unsigned long long)u.y * (unsigned)popc32((unsigned)mask)) >> 32);
+      int pick = (int)(((unsigned long long)uy * (unsigned)popc32((unsigned)mask)) >> 32);
       unsigned mm = (unsigned)mask;
       SFL_NU
       for (; pick > 0; pick--) mm &= mm - 1;
@@ -750,6 +762,7 @@ SFL_NI void env_reset(Env e, const Grp<G> &g, int on) {
     }
     h->elapsed = 0; h->step_counter = 0; h->num_malf = 0; h->terminated = 0; h->truncated = 0; h->need_reset = 0;
     h->pending_fin = -1; h->cur_dec = -1; h->ev_cursor = 0; h->active_mask = 0; h->malf_prev_mask = 0; h->at_dest_mask = 0;
+    h->eps_tag = -1;
     h->done_mask = 0; h->cum_reward = 0.0;
   }
   g.sync();
