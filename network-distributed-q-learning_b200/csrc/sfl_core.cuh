@@ -3,12 +3,13 @@
 // Restates (not ports) rows E1-E7, O1-O3, R1, Q1-Q3, F1-F5 of SURVEY.md section 8a for a batched,
 // structure-of-arrays device layout.  Citations "file:line" are relative to the reference repository.
 //
-// Execution model: a GROUP of G lanes (G = 1, 2, 4, ... 32, a template parameter chosen per launch from the
-// batch size) owns one environment for the whole launch; 32/G environments share a warp.  The per-tick train
-// phase is lane-parallel inside the group (lane = train, strided for T > G) with group-masked warp reductions;
-// the per-decision phase is inherently serial inside an environment (every _apply_action mutates the semaphores
-// the next observe reads, switch_env.py:648) and runs on the group's first lane.  Every group executes the same
-// number of loop iterations per launch, so the groups of a warp re-converge each iteration.
+// Execution model: a GROUP of G lanes (G = 1, 2, 4, ... 32, a template parameter chosen per launch from the batch
+// size) owns one environment for the whole launch; 32/G environments share a warp and ONE instruction stream: every
+// sync and vote is issued by the whole warp at warp-uniform points of the control flow, the groups differ only in
+// their predicates (see Grp below).  The per-tick train phase is lane-parallel inside the group (lane = train, in
+// chunks of G when T > G); the per-decision phase is inherently serial inside an environment (every _apply_action
+// mutates the semaphores the next observe reads, switch_env.py:648) and runs on the group's first lane -- for all
+// groups of the warp at once.  What a launch cannot need is compiled out (kernel KIND, TH, SQ, ONE: DESIGN.md section 4).
 //
 // The same source compiles for a single "lane" on the host: tests/emul builds it with g++ (-DSFL_HOST_EMUL) to
 // unit-test the logic on the CPU box that has no GPU.  That build is test infrastructure; the product library
