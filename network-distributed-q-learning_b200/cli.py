@@ -2,6 +2,7 @@
 
     python -m switchfl_b200.cli -c config.ini                 # main.py:83-88, same INI schema
     launch_grid(hyperparams, random_seeds, out_dir, ...)      # hyperparam_tuning.py:42-91 without the process fan-out
+    launch_eval(exp_dir_list)                                 # eval.py:31-97
 
 ``config.ini`` keeps the reference's sections and keys (hyperparam_tuning.py:51-78): MISC{random_seed, out_dir,
 checkpoint_freq, exploit_freq}, ENV{width, height, max_num_cities, max_rails_between_cities, max_rail_pairs_in_city,
@@ -109,6 +110,38 @@ def launch_grid(hyperparams: Dict[str, Sequence[float]], random_seeds: Sequence[
             written.append(exp_dir)
         env.engine.close()
     return written
+
+
+def launch_eval(exp_dir_list: Sequence[str], distr_q_model_name: str = "distr_q_model.pkl", device: str = "cuda:0",
+                _engine_kwargs=None) -> Dict[str, np.ndarray]:
+    """eval.py:31-97: for every experiment directory reload ``config.ini`` + the pickled Q-table and run the greedy
+    ``test()`` -- once, or ten times when the map has malfunctions (eval.py:88).  The evaluations are the environment
+    axis of one engine (environment i draws its malfunctions from seed + i) and go to ``eval_i/`` like the reference's."""
+    out = {}
+    for exp_dir in exp_dir_list:
+        print(f"Evaluating {exp_dir}")
+        config = configparser.ConfigParser()
+        config.read(os.path.join(exp_dir, "config.ini"))
+        envs, mdl, seed = config["ENV"], config["MODEL"], int(config["MISC"]["random_seed"])
+        rate = float(envs["malfunction_rate"])
+        mf = ParamMalfunctionGen(MalfunctionParameters(rate, int(envs["min_duration"]), int(envs["max_duration"])))
+        num_evals = 10 if rate > 0 else 1
+        env = ASyncSwitchEnv(RailEnv(fixture_from_env_section(dict(envs), seed), malfunction_generator=mf), render_mode=None,
+                             max_steps=100_000, n_envs=num_evals, device=device, _engine_kwargs=_engine_kwargs)
+        model = DistrQLearning(env=env, gamma=float(mdl["gamma"]), epsilon=float(mdl["epsilon"]),
+                               epsilon_decay_rate=float(mdl["epsilon_decay_rate"]), lr=float(mdl["lr"]),
+                               lr_decay_rate=float(mdl["lr_decay_rate"]), default_q=float(mdl["default_q"]), seed=seed)
+        model.load(os.path.join(exp_dir, distr_q_model_name))
+        cum, arrived, delays = model.test(out_dir=None, plot=False, save_outputs=False, _batched=True)
+        for i in range(num_evals):
+            print(f"Eval {i+1}")
+            d = os.path.join(exp_dir, f"eval_{i}")
+            os.makedirs(d, exist_ok=True)
+            np.savez_compressed(os.path.join(d, "cum_reward.npz"), x=cum[i])                 # distr_q.py:237-239
+            np.savez_compressed(os.path.join(d, "delays.npz"), x=list(delays[i]))
+        out[exp_dir] = np.stack([cum, arrived])
+        env.engine.close()
+    return out
 
 
 def main(argv=None):

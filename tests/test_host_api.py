@@ -261,6 +261,10 @@ def test_grid_launcher_writes_the_reference_tree():
                                random_seeds=[64, 65], out_dir=tmp, env_section=env_section, num_episodes=3, checkpoint_freq=10 ** 9,
                                exploit_freq=None, _engine_kwargs={"_emul_lib": emul})
         assert sorted(os.path.relpath(d, tmp) for d in dirs) == ["exp_0/seed_0", "exp_0/seed_1", "exp_1/seed_0", "exp_1/seed_1"]
+        res = cli.launch_eval(dirs[:2], _engine_kwargs={"_emul_lib": emul})                       # eval.py:31-97
+        for d in dirs[:2]:
+            assert res[d].shape == (2, 1) and np.load(os.path.join(d, "eval_0", "cum_reward.npz"))["x"].shape == ()
+            assert len(np.load(os.path.join(d, "eval_0", "delays.npz"))["x"]) == 2
         for d in dirs:
             c = configparser.ConfigParser()
             c.read(os.path.join(d, "config.ini"))
