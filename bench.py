@@ -239,7 +239,8 @@ def run_ours(args):
 
     # ---------------- device-resident arm: Engine level, CUDA-event timed (one engine per map, one stream)
     rms = [backend.RailMap(fx) for fx in fxs]
-    engs = [backend.Engine(rm, n_envs=Bp, device=dev, q_cap=args.q_cap, ep_cap=4, lanes=args.lanes or None, shared_q=SHARED_Q) for rm in rms]
+    engs = [backend.Engine(rm, n_envs=Bp, device=dev, q_cap=args.q_cap, ep_cap=4, lanes=args.lanes or None, shared_q=SHARED_Q,
+                           cta_warps=args.cta_warps or None) for rm in rms]
     lanes = engs[0].lanes
     for k, eng in enumerate(engs):
         eng.set_hparams(**HP, seeds=seeds_of(k), episodes=-1)
@@ -303,7 +304,7 @@ def run_ours(args):
     models = []
     for k, fx in enumerate(fxs):
         env = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=Bp, device=dev, q_cap=args.q_cap, ep_cap=4,
-                                 shared_q=SHARED_Q, _engine_kwargs={"lanes": args.lanes or None})
+                                 shared_q=SHARED_Q, _engine_kwargs={"lanes": args.lanes or None, "cta_warps": args.cta_warps or None})
         models.append(api.DistrQLearning(env=env, seeds=seeds_of(k), dist=dist, **HP))
     for _ in range(args.warmup):
         for m in models:
@@ -386,6 +387,7 @@ def main():
     ap.add_argument("--ticks", type=int, default=512, help="flatland ticks per env per step (launch)")
     ap.add_argument("--q-cap", type=int, default=0, help="Q hash rows per environment (0 = the workload's own)")
     ap.add_argument("--lanes", type=int, default=0, help="lanes of a warp per environment (0 = library default for the batch size)")
+    ap.add_argument("--cta-warps", type=int, default=0, help="warps per CTA of the hot-path kernel (0 = library default)")
     ap.add_argument("--cpu-seconds", type=float, default=3.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -189,6 +189,9 @@ int sfl_reset(void *ctx, int keep_q, void *stream);
  * batch ~3.5 warps per SM scheduler); this overrides it.  A scheduling choice only: results do not depend on it.  */
 int sfl_set_lanes(void *ctx, int lanes);
 int sfl_get_lanes(void *ctx);
+/* Warps per CTA of the hot-path kernel: 0 = automatic (4, halved while the launch has fewer than 8 CTAs per SM), or 1, 2,
+ * 4.  A scheduling choice only.                                                                        */
+int sfl_set_cta_warps(void *ctx, int warps);
 
 /* enable the optimistic initialisation of distr_q.py:299-300 for rows created from now on           */
 int sfl_enable_q_init(void *ctx, int on);

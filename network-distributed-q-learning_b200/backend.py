@@ -89,6 +89,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sfl_enable_q_init.argtypes = [C.c_void_p, C.c_int]
     lib.sfl_set_lanes.argtypes = [C.c_void_p, C.c_int]
     lib.sfl_get_lanes.argtypes = [C.c_void_p]
+    lib.sfl_set_cta_warps.argtypes = [C.c_void_p, C.c_int]
     lib.sfl_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.sfl_total_decisions.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
     lib.sfl_export_q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.c_void_p]
@@ -221,7 +222,7 @@ class Engine:
     def __init__(self, rail_map: RailMap, n_envs: int, device: str = "cuda:0", q_cap: int = 1024, pend_cap: int = 8,
                  max_steps: int = 100_000, dec_cap: int = 0, tick_cap: int = 0, ep_cap: int = 64, act_cap: int = 0,
                  ev_cap: int = 0, trace_sem: bool = False, lanes: Optional[int] = None, shared_q: bool = False,
-                 _emul_lib: Optional[str] = None):
+                 cta_warps: Optional[int] = None, _emul_lib: Optional[str] = None):
         import torch
         self.torch = torch
         self.map = rail_map
@@ -256,6 +257,8 @@ class Engine:
         self._ck(self.lib.sfl_bind(self.ctx, C.byref(b)))
         if lanes is not None:
             self._ck(self.lib.sfl_set_lanes(self.ctx, int(lanes)))
+        if cta_warps is not None:
+            self._ck(self.lib.sfl_set_cta_warps(self.ctx, int(cta_warps)))
         self.hparams = np.zeros(self.n_envs, HPARAMS_DT)
         self._pinned = {}
 

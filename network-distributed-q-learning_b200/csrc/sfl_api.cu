@@ -52,7 +52,9 @@ static int dev_zero(void *d, size_t n, void *) { memset(d, 0, n); return 0; }
 #ifndef SFL_MINB_BIG
 #define SFL_MINB_BIG 7                                 // CTAs per SM the large-map (tail in HBM) kernels are compiled for
 #endif
+#ifndef SFL_WARPS_PER_CTA
 #define SFL_WARPS_PER_CTA 4
+#endif
 #define SFL_CTA_THREADS (32 * SFL_WARPS_PER_CTA)
 #define SFL_SMEM_BUDGET (56u * 1024u)                  // per CTA, so that four CTAs share an SM
 
@@ -96,8 +98,10 @@ __global__ void __launch_bounds__(SFL_CTA_THREADS) k_init(InitArgs ia) {
 // environment: [hot env state (hot_bytes) | sfl_hparams | Scratch]; the hot state (header, train records, pending
 // lists and -- when they fit -- semaphores, rewards and per-switch counters) is staged once per launch and written
 // back at the end, so the tick / decision loops touch HBM only for Q rows.
-template <int G, int KIND, bool TH, bool SQ, bool ONE>
-__global__ void __launch_bounds__(SFL_CTA_THREADS, TH ? (G == 32 ? 7 : 4) : SFL_MINB_BIG) k_run() {
+// ROOMY: compiled for 4 instead of 7 CTAs per SM (about 100 instead of 72 registers, no spills) -- for launches of the
+// large-map kernels that do not fill the SMs anyway (C3: 1024 one-environment warps per map, +10 %).
+template <int G, int KIND, bool TH, bool SQ, bool ONE, bool ROOMY = false>
+__global__ void __launch_bounds__(SFL_CTA_THREADS, TH ? (G == 32 ? 7 : 4) : (ROOMY ? 4 : SFL_MINB_BIG)) k_run() {
   const int slot = threadIdx.x / G;                    // environment slot inside the CTA
   const int env_id = blockIdx.x * (blockDim.x / G) + slot;
   env_run<G, KIND, TH, SQ, ONE>(env_id, (unsigned)slot * c_ra.env_smem, nullptr);
@@ -157,7 +161,9 @@ __global__ void __launch_bounds__(512) k_distance_map(const uint16_t *grid, int 
 typedef void (*run_kernel_t)();
 // `one`: every train has its own lane (T <= G): the production kernels have a single-pass variant for that; the full and
 // the shared-table kernels always run the general chunked loops.
-template <int G> static run_kernel_t pick_kernel_g(int kind, int th, int sq, int one) {
+template <int G> static run_kernel_t pick_kernel_g(int kind, int th, int sq, int one, int roomy) {
+  if (roomy && !th && !sq && kind == K_LEARN && G >= 16)                                 // the only roomy instantiations
+    return one ? k_run<(G >= 16 ? G : 32), K_LEARN, false, false, true, true> : k_run<(G >= 16 ? G : 32), K_LEARN, false, false, false, true>;
   if (sq) {                                                                              // shared-table variants: learn / greedy only
     if (kind == K_GREEDY) return th ? k_run<G, K_GREEDY, true, true, false> : k_run<G, K_GREEDY, false, true, false>;
     return th ? k_run<G, K_LEARN, true, true, false> : k_run<G, K_LEARN, false, true, false>;
@@ -168,14 +174,14 @@ template <int G> static run_kernel_t pick_kernel_g(int kind, int th, int sq, int
   return th ? (one ? k_run<G, K_LEARN, true, false, true> : k_run<G, K_LEARN, true, false, false>)
             : (one ? k_run<G, K_LEARN, false, false, true> : k_run<G, K_LEARN, false, false, false>);
 }
-static run_kernel_t pick_kernel(int G, int kind, int th, int sq, int one) {
+static run_kernel_t pick_kernel(int G, int kind, int th, int sq, int one, int roomy) {
   switch (G) {
-    case 1: return pick_kernel_g<1>(kind, th, sq, one);
-    case 2: return pick_kernel_g<2>(kind, th, sq, one);
-    case 4: return pick_kernel_g<4>(kind, th, sq, one);
-    case 8: return pick_kernel_g<8>(kind, th, sq, one);
-    case 16: return pick_kernel_g<16>(kind, th, sq, one);
-    default: return pick_kernel_g<32>(kind, th, sq, one);
+    case 1: return pick_kernel_g<1>(kind, th, sq, one, roomy);
+    case 2: return pick_kernel_g<2>(kind, th, sq, one, roomy);
+    case 4: return pick_kernel_g<4>(kind, th, sq, one, roomy);
+    case 8: return pick_kernel_g<8>(kind, th, sq, one, roomy);
+    case 16: return pick_kernel_g<16>(kind, th, sq, one, roomy);
+    default: return pick_kernel_g<32>(kind, th, sq, one, roomy);
   }
 }
 #endif
@@ -186,7 +192,7 @@ struct Ctx {
   Layout L;
   sfl_config cfg;
   sfl_buffers bufs;
-  int bound, device, q_init_on, lanes, sm_count;
+  int bound, device, q_init_on, lanes, sm_count, cta_warps;
   unsigned hot_bytes, env_smem, tail_hot;
   void *blob;          // device block holding every map table
   void *sum_buf;       // 2 x u64
@@ -374,7 +380,7 @@ int sfl_create(const sfl_map_desc *map, const sfl_config *cfg, int device, void 
 #endif
   Ctx *c = new (std::nothrow) Ctx();
   if (!c) return fail(SFL_E_NOMEM, "host alloc%s");
-  c->L = L; c->cfg = *cfg; c->bound = 0; c->device = device; c->q_init_on = 0; c->blob = nullptr; c->sum_buf = nullptr; c->sm_count = sm_count;
+  c->L = L; c->cfg = *cfg; c->bound = 0; c->device = device; c->q_init_on = 0; c->cta_warps = 0; c->blob = nullptr; c->sum_buf = nullptr; c->sm_count = sm_count;
   memset(&c->bufs, 0, sizeof(c->bufs));
   auto pcell = [&](int cell) { return cell < 0 ? -1 : (cell / W + 1) * Wp + (cell % W + 1); };
   // ---- pack every table into one host image, 16-byte aligned sections
@@ -482,6 +488,14 @@ int sfl_set_lanes(void *ctx, int lanes) {
   return SFL_OK;
 }
 
+int sfl_set_cta_warps(void *ctx, int warps) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c) return fail(SFL_E_ARG, "null ctx%s");
+  if (warps != 0 && warps != 1 && warps != 2 && warps != 4) return fail(SFL_E_ARG, "warps per CTA must be 0 (automatic), 1, 2 or 4%s");
+  c->cta_warps = warps;
+  return SFL_OK;
+}
+
 int sfl_get_lanes(void *ctx) {
   Ctx *c = (Ctx *)ctx;
   return c ? c->lanes : SFL_E_ARG;
@@ -542,14 +556,23 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   const int kind = trace ? K_FULL : (mode == SFL_MODE_GREEDY ? K_GREEDY : K_LEARN);
 #ifndef SFL_HOST_EMUL
   const int G = c->lanes;
-  int threads = SFL_CTA_THREADS;                       // shrink the CTA until its environments fit shared memory
+  // Warps per CTA: the kernels are compiled for at most SFL_WARPS_PER_CTA; small launches use smaller CTAs so that the
+  // CTAs spread evenly over the SMs (1024 one-env warps as 256 CTAs leave SMs with 8 or 4 warps; as 1024 CTAs with 7).
+  int cta_warps = c->cta_warps;
+  if (cta_warps <= 0) {
+    const long warps = ((long)c->cfg.n_envs * G + 31) / 32;
+    cta_warps = SFL_WARPS_PER_CTA;
+    while (cta_warps > 1 && warps / cta_warps < 8L * c->sm_count) cta_warps /= 2;      // fewer than 8 CTAs per SM: halve
+  }
+  int threads = 32 * cta_warps;                        // then shrink the CTA until its environments fit shared memory
   while (threads > 32 && (size_t)c->env_smem * (threads / G) > SFL_SMEM_BUDGET) threads /= 2;
   const int envs_per_cta = threads / G;
   const size_t smem = (size_t)c->env_smem * envs_per_cta;
   if (smem > 227u * 1024u) return fail(SFL_E_ARG, "environment state does not fit shared memory with this many lanes per env: use more lanes%s");
   int grid = (c->cfg.n_envs + envs_per_cta - 1) / envs_per_cta;
   if (c->cfg.shared_q && trace) return fail(SFL_E_ARG, "shared-table mode has no trace / step variants%s");
-  run_kernel_t k = pick_kernel(G, kind, (int)c->tail_hot, c->cfg.shared_q, c->L.T <= G);
+  const int roomy = ((long)c->cfg.n_envs * G + 31) / 32 <= 16L * c->sm_count;            // one wave even at 4 CTAs per SM
+  run_kernel_t k = pick_kernel(G, kind, (int)c->tail_hot, c->cfg.shared_q, c->L.T <= G, roomy);
   CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(set_constants(c, &ra, stream));
   k<<<grid, threads, smem, (cudaStream_t)stream>>>();
