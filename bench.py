@@ -38,10 +38,10 @@ SEED = 450565
 WORKLOADS = {
     "c2": ("c1_synth18", 4096, 1024,
            "C2: 4096 lockstep envs of the test_model.py map (c1_synth18 stand-in), distributed Q-learning, learn mode"),
-    "c3": ("@c3", 5120, 32768,
+    "c3": ("@c3", 20480, 32768,
            "C3: hyperparam_tuning.py default grid (eps .5, decay .9997, lr .1) x seeds {64,65,66,67,69} = 5 maps (80x80, 15 trains, "
            "25 cities, no malfunctions; synthetic stand-ins), each (map, point) replicated with distinct RNG streams: "
-           "5 x 1024 envs per GPU, distributed Q-learning, learn mode"),
+           "5 x 4096 envs per GPU, distributed Q-learning, learn mode"),
     "c4": ("c4_synth100_t50", 8192, 65536,
            "C4: large synthetic map (100x100, 50 trains, 281 switches, malfunctions), 65536 envs per 8 GPUs = 8192 per GPU, "
            "distributed Q-learning, learn mode"),
