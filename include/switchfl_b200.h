@@ -9,7 +9,9 @@
  * bulk buffers are CALLER-OWNED device pointers (the Python host allocates them as torch tensors) and
  * the library never frees them; only the small map-constant block is owned by the context.  One
  * context per GPU per map, driven from one host thread; work is enqueued on the caller's stream
- * (a cudaStream_t passed as void*).  There is no CPU path: without a CUDA device sfl_create fails.
+ * (a cudaStream_t passed as void*).  Several contexts (maps) may live in one process, but all of them must be driven on
+ * ONE stream: the map / layout / launch constants of a launch sit in __constant__ memory, written in stream order just
+ * before it.  There is no CPU path: without a CUDA device sfl_create fails.
  */
 #ifndef SWITCHFL_B200_H
 #define SWITCHFL_B200_H
