@@ -340,3 +340,33 @@ def test_cuda_production_kernels_equal_the_full_kernel(name, lanes):
         assert np.array_equal(a[0][k], b[0][k]) and np.array_equal(a[3][k], b[3][k]), k
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
     assert a[6] == b[6]
+
+
+@pytest.mark.parametrize("name", ["c1_synth18", "slips24_t6"])
+def test_cuda_free_running_learn_equals_the_host_build(name):
+    """Free-running learn (Philox epsilon-greedy and malfunction draws included) on the device against the same sources
+    compiled for the host (tests/emul): identical counters, episode logs and Q-tables for identical seeds."""
+    from tests.test_emul_parity import build_emul
+    emul = build_emul()
+    fx, _ = load_golden(name)
+    rm = backend.RailMap(fx)
+    hp = dict(gamma=0.95, epsilon=0.5, epsilon_decay_rate=0.999, lr=0.2, lr_decay_rate=1.0, default_q=0.0)
+    B, n_ep = 12, 4
+    out = []
+    for kw in (dict(device="cuda:0"), dict(_emul_lib=emul)):
+        eng = backend.Engine(rm, n_envs=B, q_cap=4096, ep_cap=8, **kw)
+        eng.set_hparams(**hp, seeds=np.arange(B) + 31, episodes=n_ep)
+        eng.reset()
+        eng.enable_q_init(True)
+        for _ in range(40):                                           # several launches: the streams do not depend on the cut
+            eng.run(backend.MODE_LEARN, 97)
+        eng.check_errors(allow=backend.ERR_NO_TRAIN_AT_SWITCH)
+        c = eng.counters().copy()
+        _, log, dl = eng.episode_log()
+        out.append((c, log[:, :n_ep].copy(), dl[:, :n_ep].copy(), [eng.export_q(i) for i in range(B)]))
+        eng.close()
+    (c1, l1, d1, q1), (c2, l2, d2, q2) = out
+    assert (c1["halted"] == 1).all()
+    for k in ("decisions", "ticks", "train_ticks", "episodes", "err", "q_rows", "aborted"):
+        assert np.array_equal(c1[k], c2[k]), k
+    assert np.array_equal(l1, l2) and np.array_equal(d1, d2) and q1 == q2
