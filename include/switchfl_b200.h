@@ -174,13 +174,14 @@ int sfl_distance_map(const uint16_t *grid, int32_t H, int32_t W, const int32_t *
 int sfl_abi_version(void);
 const char *sfl_last_error(void);
 
-/* sizes of everything the caller must allocate */
+/* Sizes of everything the caller must allocate.  No counterpart in the reference, where the Python objects own their
+ * memory (env: switch_env.py:42-73, learner: distr_q.py:33-57); here PyTorch does, and the library is told how much.  */
 int sfl_query_sizes(const sfl_map_desc *map, const sfl_config *cfg, sfl_sizes *out);
 
 /* replaces ASyncSwitchEnv(rail_env, ...) + DistrQLearning(env, ...)   (main.py:51-60) */
 int sfl_create(const sfl_map_desc *map, const sfl_config *cfg, int device, void **ctx);
-int sfl_destroy(void *ctx);
-int sfl_bind(void *ctx, const sfl_buffers *bufs);
+int sfl_destroy(void *ctx);                       /* env.close() (switch_env.py, called at distr_q.py:241, 379) + garbage collection */
+int sfl_bind(void *ctx, const sfl_buffers *bufs); /* hand over the caller-owned device buffers sized by sfl_query_sizes            */
 
 /* zero state + mark every env "needs reset"; the first sfl_run performs env.reset (switch_env.py:93-158)
  * on the device.  keep_q != 0 keeps Q tables and interaction counters (a new learn()/test() call).     */
@@ -207,7 +208,8 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream);
  * independent, bit-reproducible) before calling this, which leaves identical tables on every rank.                 */
 int sfl_shared_q_apply(void *ctx, void *stream);
 
-/* sum of decisions over all envs after the last run (device reduction, 8-byte D2H)                   */
+/* Sum over all envs of the decisions taken (num_iter, distr_q.py:284, 361) and of the flatland ticks
+ * (rail_env._elapsed_steps) after the last run: device reduction, 16-byte D2H.                         */
 int sfl_total_decisions(void *ctx, uint64_t *decisions, uint64_t *ticks, void *stream);
 
 /* Q-table export for distr_q_model.pkl (distr_q.py:492-523): rows of env `env` as (key, A_max values) */
