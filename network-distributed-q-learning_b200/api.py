@@ -399,6 +399,47 @@ class DistrQLearning:
         self.q_table = eng.export_q(p, include_init=self._q_inited, default_q=self._default_q_of(p))   # test() inserts rows (App. A #15)
         return float(cum[p]), int(arr[p]), list(delays[p])
 
+    # ------------------------------------------------------------------ distr_q.py:400-490, on the host dict
+    # The reference's per-decision learner methods, for code that drives the AEC protocol itself (env.agent_iter /
+    # last / step) and keeps the learning rule on the host.  They work on ``self.q_table`` exactly like the reference
+    # (keys: observation tuples; rows: lists of floats; rows appear on first lookup); ``learn()`` / ``test()`` do the same
+    # work on the device and overwrite ``q_table`` with the device tables when they finish.
+    def _check_entry(self, state, agent) -> list:
+        key = tuple(int(x) for x in state)
+        row = self.q_table.get(key)
+        if row is None:                                                    # distr_q.py:47-57
+            row = self.q_table[key] = [self._default_q_of(self.primary_env)] * self.env.action_space(agent).n
+        return row
+
+    def eval(self, state, action, agent) -> float:                         # distr_q.py:400-417
+        return self._check_entry(state, agent)[action]
+
+    def max_q(self, state, agent) -> float:                                # distr_q.py:449-466 (ignores the action mask)
+        if state is None:
+            return 0.0
+        return max(self._check_entry(state, agent))
+
+    def max_action(self, state, agent, action_mask) -> int:                # distr_q.py:468-490
+        row = self._check_entry(state, agent)
+        best = int(np.argmax(row))
+        if action_mask[best]:
+            return best
+        allowed = np.nonzero(action_mask)[0]
+        return int(allowed[np.argmax(np.array(row)[allowed])])
+
+    def update(self, state, action, reward, next_state, previous_agent, next_agent, agent_num_interactions):
+        """distr_q.py:419-447: Q <- (1 - lr) Q + lr (r + gamma max_a' Q(s', a')), without the bootstrap when the train
+        stayed at the same switch; lr = lr0 * lr_decay_rate ** (interactions of the previous switch)."""
+        row = self._check_entry(state, previous_agent)
+        lr0 = float(np.asarray(self.initial_lr, np.float64).reshape(-1)[0])
+        decay = float(np.asarray(self.lr_decay_rate, np.float64).reshape(-1)[0])
+        gamma = float(np.asarray(self.gamma, np.float64).reshape(-1)[0])
+        lr = lr0 * (decay ** agent_num_interactions[previous_agent])
+        if next_agent != previous_agent:
+            row[action] = (1 - lr) * row[action] + lr * (reward + gamma * self.max_q(next_state, next_agent))
+        else:
+            row[action] = (1 - lr) * row[action] + lr * reward
+
     # ------------------------------------------------------------------ distr_q.py:492-527
     def save(self, filename: str, mode: str = "pickle"):
         if mode != "pickle":

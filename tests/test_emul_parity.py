@@ -274,3 +274,44 @@ def test_emul_malfunction_draws_have_the_flatland_distribution(emul_lib):
     assert durs[:6].sum() == 0 and len(durs) == 17                         # 5..15 + 1
     expect = new.sum() / 11
     assert (np.abs(durs[6:17] - expect) < 5 * np.sqrt(expect)).all()
+
+
+def test_emul_reference_loop_with_the_drop_in_learner_methods(emul_lib):
+    """distr_q.py:296-362 written against the drop-in classes only -- env.reset / agent_iter / last / step and
+    model.update / max_q / max_action, actions replayed from the golden -- ends with the reference's Q-table."""
+    import numpy as np
+    from switchfl_b200 import api
+    from tests._util import hparams, q_dict
+    env, g = _aec_env("c1_synth18", emul_lib)
+    hp = hparams(g)
+    model = api.DistrQLearning(env=env, seed=int(g["seed"]), **hp)
+    model.q_table = dict(env.rail_map.q_init_rows(hp["default_q"]))                             # __init_q_table (:299-300)
+    ninter = {a: 0 for a in env.possible_agents}
+    i = 0
+    for ep in range(int(g["n_episodes"])):
+        env.reset(seed=int(g["seed"]))
+        update_dict, at_dest = {}, []
+        for agent in env.agent_iter():
+            obs, R, term, trunc, info = env.last()
+            train = info["active_train"]
+            action = int(g["dec_action"][i])
+            if g["dec_greedy"][i]:                                                               # the exploit branch (:318-319)
+                assert model.max_action(obs, agent, info["action_mask"]) == action
+            post = env.step(action)
+            nxt = "switch_%d-%d" % post["next_switch"]
+            if (agent, train) in update_dict:
+                pobs, pact, pagent = update_dict.pop((agent, train))
+                model.update(pobs, pact, R[train], obs, pagent, agent, ninter)
+            update_dict[(nxt, train)] = (obs, action, agent)
+            for h in post["arrived_trains"]:
+                if h not in at_dest:
+                    at_dest.append(h)
+                    for k in [k for k in update_dict if k[1] == h]:
+                        pobs, pact, pagent = update_dict.pop(k)
+                        model.update(pobs, pact, 1000.0, None, pagent, None, ninter)
+            ninter[agent] += 1
+            i += 1
+    assert i == len(g["dec_action"])
+    assert model.q_table == q_dict(g["q_keys"], g["q_vals"])
+    assert model.eval(g["dec_obs"][0][g["dec_obs"][0] != -9], 0, env.possible_agents[int(g["dec_switch"][0])]) == \
+        q_dict(g["q_keys"], g["q_vals"])[tuple(int(x) for x in g["dec_obs"][0] if x != -9)][0]
