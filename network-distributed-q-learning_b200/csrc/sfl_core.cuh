@@ -148,7 +148,9 @@ struct EnvHdr {            // 128 bytes at the start of every env block
 //   TrB {prev_port (u16) | source_port<<16 (0xFFFF = none), act_switch (u16) | pend_n<<16, last_delay, 0}
 // Per-switch record SwS {interactions, 0, eps_pow (f64) = epsilon_decay_rate ** interactions}.
 // Pending update (distr_q.py:340-342): {key, next_sw | prev_sw<<12 | action<<24}; part of the tail (decision phase only).
-// Semaphore record (rail_network.py:133): {t0, t1, train (-1 = absent), type}.
+// Semaphore record (rail_network.py:133 [train, in/out, dir, t0, t1]): {t0, t1 - t0, train (-1 = absent), type} -- start
+// and LENGTH of the window, so that extend_semaphores (rail_network.py:229-244: slide the window to start now, keep its
+// length) is one 4-byte store per record and needs no load.
 struct SwS { int ninter, pad; double eps_pow; };
 
 struct RunArgs {           // per-launch arguments
@@ -290,12 +292,12 @@ SFL_FN int rule_port(Env e, int port, int me, int now, int blocking_type) {
   int4 r;
   if (Env::HOT_TAIL) {                                                        // staged table: one shared-memory load
     r = e.sem()[port];
-    if (r.z < 0 || r.z == me || r.x > now || r.y < now) return 0;
+    if (r.z < 0 || r.z == me || r.x > now || r.x + r.y < now) return 0;
   } else {                                                              // table in HBM: ask the holder mirror first
     const int holder = e.owner(port);
     if (holder < 0 || holder == me) return 0;
     r = e.sem()[port];
-    if (r.x > now || r.y < now) return 0;
+    if (r.x > now || r.x + r.y < now) return 0;
   }
   if (r.w == blocking_type) return 1;
   return tr_state(e, r.z) == ST_MALF;
@@ -435,56 +437,56 @@ SFL_FN void transition_semaphore(Env e, int source, int out_port, int target, in
   }
   if (Env::HOT_TAIL) {                                                        // staged table: load, test, store
     int4 r = e.sem()[out_port];                                           // :326-334
-    if (r.z < 0) e.sem()[out_port] = make_int4(now, now + 3, h, SEM_OUT);
-    else if (r.w == SEM_OUT || r.x > now) e.sem()[out_port] = make_int4(now, now + 3, h, r.w);
+    if (r.z < 0) e.sem()[out_port] = make_int4(now, 3, h, SEM_OUT);
+    else if (r.w == SEM_OUT || r.x > now) e.sem()[out_port] = make_int4(now, 3, h, r.w);
     int d_ot = c_m.port[out_port].y;
     r = e.sem()[target];                                                  // :336-344
-    if (r.z < 0) e.sem()[target] = make_int4(now, now + d_ot + 1, h, SEM_IN);
-    else if (r.w == SEM_IN || r.x > now) e.sem()[target] = make_int4(now, now + d_ot + 1, h, r.w);
+    if (r.z < 0) e.sem()[target] = make_int4(now, d_ot + 1, h, SEM_IN);
+    else if (r.w == SEM_IN || r.x > now) e.sem()[target] = make_int4(now, d_ot + 1, h, r.w);
     int unique = c_m.port[target].z;
     if (unique >= 0) {                                                    // :356 forced path through the next switch
       int4 up = c_m.port[unique];
       int far_port = up.x;
       if (unique != source && unique != out_port && unique != target) {   // :368-378
         r = e.sem()[unique];
-        if (r.z < 0 || r.w == SEM_OUT || r.x > now) e.sem()[unique] = make_int4(now, now + d_ot + 1, h, SEM_OUT);
+        if (r.z < 0 || r.w == SEM_OUT || r.x > now) e.sem()[unique] = make_int4(now, d_ot + 1, h, SEM_OUT);
       }
       r = e.sem()[unique];                                                // :380-388 (the list == 'out' test is never true)
-      if (r.z < 0 || r.x > now) e.sem()[unique] = make_int4(now, now + d_ot, h, SEM_OUT);
+      if (r.z < 0 || r.x > now) e.sem()[unique] = make_int4(now, d_ot, h, SEM_OUT);
       if (far_port != source && far_port != out_port && far_port != unique) {   // :390-402
         r = e.sem()[far_port];
-        if (r.z < 0 || r.w == SEM_IN || r.x > now) e.sem()[far_port] = make_int4(now, now + d_ot + up.y + 1, h, SEM_IN);
+        if (r.z < 0 || r.w == SEM_IN || r.x > now) e.sem()[far_port] = make_int4(now, d_ot + up.y + 1, h, SEM_IN);
       }
     }
     if (target != source && target != out_port) {                         // :404-414 moving edge
       r = e.sem()[target];
-      if (r.z < 0 || r.w == SEM_OUT || r.x > now) e.sem()[target] = make_int4(now, now + d_ot + 1, h, SEM_OUT);
+      if (r.z < 0 || r.w == SEM_OUT || r.x > now) e.sem()[target] = make_int4(now, d_ot + 1, h, SEM_OUT);
     }
   } else {                                                              // table in HBM: the holder mirror answers "nobody" without a load
     int4 r;                                                             // :326-334
-    if (e.owner(out_port) < 0) e.sem_put(out_port, make_int4(now, now + 3, h, SEM_OUT));
-    else { r = e.sem()[out_port]; if (r.w == SEM_OUT || r.x > now) e.sem_put(out_port, make_int4(now, now + 3, h, r.w)); }
+    if (e.owner(out_port) < 0) e.sem_put(out_port, make_int4(now, 3, h, SEM_OUT));
+    else { r = e.sem()[out_port]; if (r.w == SEM_OUT || r.x > now) e.sem_put(out_port, make_int4(now, 3, h, r.w)); }
     int d_ot = c_m.port[out_port].y;
-    if (e.owner(target) < 0) e.sem_put(target, make_int4(now, now + d_ot + 1, h, SEM_IN));            // :336-344
-    else { r = e.sem()[target]; if (r.w == SEM_IN || r.x > now) e.sem_put(target, make_int4(now, now + d_ot + 1, h, r.w)); }
+    if (e.owner(target) < 0) e.sem_put(target, make_int4(now, d_ot + 1, h, SEM_IN));            // :336-344
+    else { r = e.sem()[target]; if (r.w == SEM_IN || r.x > now) e.sem_put(target, make_int4(now, d_ot + 1, h, r.w)); }
     int unique = c_m.port[target].z;
     if (unique >= 0) {                                                  // :356 forced path through the next switch
       int4 up = c_m.port[unique];
       int far_port = up.x;
       if (unique != source && unique != out_port && unique != target) { // :368-378
         r = e.sem()[unique];
-        if (e.owner(unique) < 0 || r.w == SEM_OUT || r.x > now) e.sem_put(unique, make_int4(now, now + d_ot + 1, h, SEM_OUT));
+        if (e.owner(unique) < 0 || r.w == SEM_OUT || r.x > now) e.sem_put(unique, make_int4(now, d_ot + 1, h, SEM_OUT));
       }
       r = e.sem()[unique];                                              // :380-388 (the list == 'out' test is never true)
-      if (e.owner(unique) < 0 || r.x > now) e.sem_put(unique, make_int4(now, now + d_ot, h, SEM_OUT));
+      if (e.owner(unique) < 0 || r.x > now) e.sem_put(unique, make_int4(now, d_ot, h, SEM_OUT));
       if (far_port != source && far_port != out_port && far_port != unique) {   // :390-402
         r = e.sem()[far_port];
-        if (e.owner(far_port) < 0 || r.w == SEM_IN || r.x > now) e.sem_put(far_port, make_int4(now, now + d_ot + up.y + 1, h, SEM_IN));
+        if (e.owner(far_port) < 0 || r.w == SEM_IN || r.x > now) e.sem_put(far_port, make_int4(now, d_ot + up.y + 1, h, SEM_IN));
       }
     }
     if (target != source && target != out_port) {                       // :404-414 moving edge
       r = e.sem()[target];
-      if (e.owner(target) < 0 || r.w == SEM_OUT || r.x > now) e.sem_put(target, make_int4(now, now + d_ot + 1, h, SEM_OUT));
+      if (e.owner(target) < 0 || r.w == SEM_OUT || r.x > now) e.sem_put(target, make_int4(now, d_ot + 1, h, SEM_OUT));
     }
   }
 }
@@ -534,7 +536,7 @@ SFL_FN void finish_decision(Env e, const Hp hp, int env_id) {
       if (c_ra.trace_sem_buf) {
         int4 *dst = c_ra.trace_sem_buf + ((size_t)env_id * c_ra.dec_cap + h->cur_dec) * c_L.NP;
         SFL_NU
-        for (int p = 0; p < c_L.NP; p++) dst[p] = e.sem()[p];
+        for (int p = 0; p < c_L.NP; p++) { int4 r = e.sem()[p]; r.y += r.x; dst[p] = r; }      // traced as {t0, t1, train, type}
       }
     }
     h->cur_dec = -1;
@@ -759,7 +761,7 @@ SFL_NI void env_reset(Env e, const Grp<G> &g, int on) {
     SFL_NU
     for (int t = 0; t < T; t++) {                                         // switch_env.py:564-568, train order
       int4 tr1 = c_m.train1[t];
-      e.sem_put(tr1.z, make_int4(tr1.x - 2, tr1.x + tr1.w, t, SEM_IN));
+      e.sem_put(tr1.z, make_int4(tr1.x - 2, tr1.w + 2, t, SEM_IN));
     }
     h->elapsed = 0; h->step_counter = 0; h->num_malf = 0; h->terminated = 0; h->truncated = 0; h->need_reset = 0;
     h->pending_fin = -1; h->cur_dec = -1; h->ev_cursor = 0; h->active_mask = 0; h->malf_prev_mask = 0; h->at_dest_mask = 0;
@@ -1013,7 +1015,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g
       while (b) {
         int t = ffs64(b); b &= b - 1;
         int4 tr1 = c_m.train1[t];
-        e.sem_put((int)((unsigned)e.tra()[t].w >> 16), make_int4(tr1.x - 2, tr1.x + tr1.w, t, SEM_IN));
+        e.sem_put((int)((unsigned)e.tra()[t].w >> 16), make_int4(tr1.x - 2, tr1.w + 2, t, SEM_IN));
       }
     }
   }
@@ -1025,10 +1027,10 @@ SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g
     for (int p = g.gl; p < NP; p += G) {
       if (Env::HOT_TAIL) {
         int4 r = e.sem()[p];
-        if (r.z >= 0 && ((stopped_bits >> r.z) & 1)) { r.y = now + (r.y - r.x); r.x = now; e.sem()[p] = r; }
+        if (r.z >= 0 && ((stopped_bits >> r.z) & 1)) e.sem()[p].x = now;
       } else {
         const int holder = e.owner(p);                                   // only the records of stopped trains leave shared memory
-        if (holder >= 0 && ((stopped_bits >> holder) & 1)) { int4 r = e.sem()[p]; r.y = now + (r.y - r.x); r.x = now; e.sem()[p] = r; }
+        if (holder >= 0 && ((stopped_bits >> holder) & 1)) e.sem()[p].x = now;      // a 4-byte store, no load
       }
     }
     g.sync();
@@ -1040,7 +1042,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g
         int4 ta = e.tra()[t];
         if (((ta.y >> 8) & 0xFF) == ST_MALF) {
           int port = (int)((unsigned)ta.w >> 16);
-          if (e.owner(port) < 0) e.sem_put(port, make_int4(now, now + c_m.train1[t].w, t, SEM_IN));
+          if (e.owner(port) < 0) e.sem_put(port, make_int4(now, c_m.train1[t].w, t, SEM_IN));
         }
       }
     }
