@@ -287,8 +287,18 @@ class Engine:
         dst.copy_(st[:raw.size], non_blocking=True)
 
     def _download(self, name: str, nbytes: Optional[int] = None) -> np.ndarray:
+        """device -> host; small buffers that are read every step (counters, step records) go through a reusable pinned
+        staging buffer, everything else through a plain copy."""
         t = self.buf[name] if nbytes is None else self.buf[name][:nbytes]
-        return t.cpu().numpy()
+        if self._emul or t.numel() > (8 << 20):
+            return t.cpu().numpy()
+        torch = self.torch
+        st = self._pinned.get("d2h:" + name)
+        if st is None or st.numel() < t.numel():
+            st = self._pinned["d2h:" + name] = torch.empty(t.numel(), dtype=torch.uint8, pin_memory=True)
+        st[:t.numel()].copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return st[:t.numel()].numpy().copy()
 
     def close(self):
         if getattr(self, "ctx", None) is not None and self.ctx:
