@@ -78,12 +78,29 @@ class RailEnv:
         return len(self.fixture["init_dir"])
 
 
+def default_q_cap(rail_map: RailMap) -> int:
+    """Q hash rows per environment when the caller gives none: the next power of two above twice the states one learner
+    can reach -- every optimistic row of distr_q.py:81-181 (load() imports all of them) plus, per (port, target) pair that
+    occurs, the 15 x 3 semaphore / delay variants the trains actually standing there can produce; capped so that the
+    state stays allocatable.  A table that still fills up is reported (SFL_ERR_Q_FULL), never silently wrong."""
+    t, tr = rail_map.tab, rail_map.trains
+    init_rows = int((np.asarray(tr.qinit_act) >= 0).sum()) * 45
+    reach = int(t.NP) * min(len(tr.targets), 4) * 12
+    want = 2 * (init_rows + reach) + 256
+    cap = 1024
+    while cap < want and cap < (1 << 20):
+        cap *= 2
+    return cap
+
+
 class ASyncSwitchEnv:
     """Batched counterpart of switch_env.py:605-678.  Holds the map tables and the engine; the AEC
     per-decision protocol (agent_iter / last / step) is executed on the device by the learner's kernel."""
 
+    engine_cls = Engine
+
     def __init__(self, rail_env: RailEnv, max_steps: int = 200, render_mode=None, observer=None, seed=None,
-                 n_envs: int = 1, device: str = "cuda:0", q_cap: int = 1024, ep_cap: int = 128, shared_q: bool = False,
+                 n_envs: int = 1, device: str = "cuda:0", q_cap: Optional[int] = None, ep_cap: int = 128, shared_q: bool = False,
                  _engine_kwargs=None):
         self.rail_env = rail_env
         self.max_steps = max_steps
@@ -92,12 +109,12 @@ class ASyncSwitchEnv:
         self.n_envs = int(n_envs)
         kw = dict(act_cap=1, shared_q=shared_q)
         kw.update(_engine_kwargs or {})
-        import torch
-        on_gpu = "_emul_lib" not in kw and torch.cuda.is_available()
-        self.rail_map = RailMap(rail_env.fixture, device_bfs=(torch.device(device).index or 0) if on_gpu else None)
+        self.rail_map = RailMap(rail_env.fixture, device_bfs=self.engine_cls.bfs_device(device))
         self.possible_agents = self.rail_map.tab.switch_names()          # switch_env.py:51-52
         self.agents = self.possible_agents
-        self.engine = Engine(self.rail_map, n_envs=self.n_envs, device=device, q_cap=q_cap, max_steps=max_steps, ep_cap=ep_cap, **kw)
+        if q_cap is None:
+            q_cap = 2 if shared_q else default_q_cap(self.rail_map)
+        self.engine = self.engine_cls(self.rail_map, n_envs=self.n_envs, device=device, q_cap=q_cap, max_steps=max_steps, ep_cap=ep_cap, **kw)
         # the seven wall-clock accumulators main.py:72-78 prints (switch_env.py:67-73); the device loop has no
         # per-phase split, so the kernel time is booked on step_time and resets on reset_total_time
         self.flatland_step_time = self.step_time = self.last_time = 0.0
@@ -453,6 +470,9 @@ class DistrQLearning:
             q = pickle.load(f)
         self.q_table = {tuple(int(x) for x in k): [float(x) for x in v] for k, v in q.items()}
         eng = self.env.engine
+        if not eng.shared_q and len(self.q_table) >= eng.cfg.q_cap:
+            raise ValueError(f"{filename}: {len(self.q_table)} rows do not fit the {eng.cfg.q_cap}-row Q tables of this env; "
+                             f"construct ASyncSwitchEnv(q_cap=...) with a power of two above {2 * len(self.q_table)}")
         self._hparams(-1)
         eng.reset()
         for i in range(self.env.n_envs):

@@ -3,9 +3,6 @@
 PyTorch only owns the device buffers (one uint8 tensor per buffer of ``sfl_buffers``); every bit of the
 hot path runs inside ``libswitchfl_b200.so`` (hand-written sm_100a CUDA).  There is no CPU fallback: if
 the library is missing or no CUDA device exists, construction raises.
-
-(``tests/emul`` builds the same C sources for the host to unit-test the per-environment logic on the
-GPU-less build box; it is reachable only through the private ``_emul_lib`` argument used by tests.)
 """
 from __future__ import annotations
 
@@ -101,10 +98,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     return lib
 
 
-def device_distance_map(grid: np.ndarray, target_cells: Sequence[int], device: int = 0, _emul_lib: Optional[str] = None) -> np.ndarray:
+def device_distance_map(grid: np.ndarray, target_cells: Sequence[int], device: int = 0, lib: Optional[C.CDLL] = None) -> np.ndarray:
     """int32[NT, H, W, 4] distance map of flatland_patch/distance_map.py:62-167 computed on the GPU (``sfl_distance_map``);
     same values as the host BFS ``railmap.distance_to`` (which the goldens pin against the vendored reference code)."""
-    lib = load_library(_emul_lib)
+    lib = lib or load_library()
     g = np.ascontiguousarray(grid, np.uint16)
     tg = np.ascontiguousarray(target_cells, np.int32)
     H, W = g.shape
@@ -222,22 +219,12 @@ class Engine:
     def __init__(self, rail_map: RailMap, n_envs: int, device: str = "cuda:0", q_cap: int = 1024, pend_cap: int = 8,
                  max_steps: int = 100_000, dec_cap: int = 0, tick_cap: int = 0, ep_cap: int = 64, act_cap: int = 0,
                  ev_cap: int = 0, trace_sem: bool = False, lanes: Optional[int] = None, shared_q: bool = False,
-                 cta_warps: Optional[int] = None, _emul_lib: Optional[str] = None):
+                 cta_warps: Optional[int] = None):
         import torch
         self.torch = torch
         self.map = rail_map
         self.n_envs = int(n_envs)
-        self._emul = _emul_lib is not None
-        if self._emul:
-            self.lib = load_library(_emul_lib)
-            self.device = torch.device("cpu")
-            dev_index = 0
-        else:
-            if not torch.cuda.is_available():
-                raise RuntimeError("switchfl_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-            self.lib = load_library()
-            self.device = torch.device(device)
-            dev_index = self.device.index or 0
+        self.lib, self.device, dev_index = self._open(device)
         self.cfg = Config(n_envs=self.n_envs, q_cap=q_cap, pend_cap=pend_cap, max_steps=max_steps, dec_cap=dec_cap,
                           tick_cap=tick_cap, ep_cap=ep_cap, act_cap=act_cap, ev_cap=ev_cap, trace_sem=int(trace_sem),
                           shared_q=int(shared_q))
@@ -261,15 +248,28 @@ class Engine:
             self._ck(self.lib.sfl_set_cta_warps(self.ctx, int(cta_warps)))
         self.hparams = np.zeros(self.n_envs, HPARAMS_DT)
         self._pinned = {}
+        self._pinned_ev = {}
 
     # ------------------------------------------------------------------ helpers
+    def _open(self, device):
+        """(library, torch device of the buffers, CUDA device index)."""
+        torch = self.torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("switchfl_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        dev = torch.device(device)
+        return load_library(), dev, dev.index or 0
+
+    @staticmethod
+    def bfs_device(device) -> Optional[int]:
+        """CUDA device index the map preprocessing (distance map) runs on."""
+        import torch
+        return torch.device(device).index or 0
+
     def _ck(self, rc: int):
         if rc != 0:
             raise RuntimeError(f"switchfl_b200 error {rc}: {self.lib.sfl_last_error().decode()}")
 
     def _stream(self):
-        if self._emul:
-            return None
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
     def _upload(self, name: str, host: np.ndarray):
@@ -277,20 +277,21 @@ class Engine:
         torch = self.torch
         raw = np.ascontiguousarray(host).view(np.uint8).reshape(-1)
         dst = self.buf[name][:raw.size]
-        if self._emul:
-            dst.copy_(torch.from_numpy(raw))
-            return
         st = self._pinned.get(name)
         if st is None or st.numel() < raw.size:
             st = self._pinned[name] = torch.empty(raw.size, dtype=torch.uint8, pin_memory=True)
+            self._pinned_ev[name] = torch.cuda.Event()
+        else:
+            self._pinned_ev[name].synchronize()            # the previous copy out of this staging buffer has finished
         st[:raw.size].copy_(torch.from_numpy(raw))
         dst.copy_(st[:raw.size], non_blocking=True)
+        self._pinned_ev[name].record(torch.cuda.current_stream(self.device))
 
     def _download(self, name: str, nbytes: Optional[int] = None) -> np.ndarray:
         """device -> host; small buffers that are read every step (counters, step records) go through a reusable pinned
         staging buffer, everything else through a plain copy."""
         t = self.buf[name] if nbytes is None else self.buf[name][:nbytes]
-        if self._emul or t.numel() > (8 << 20):
+        if t.numel() > (8 << 20):
             return t.cpu().numpy()
         torch = self.torch
         st = self._pinned.get("d2h:" + name)

@@ -7,8 +7,9 @@
 ``config.ini`` keeps the reference's sections and keys (hyperparam_tuning.py:51-78): MISC{random_seed, out_dir,
 checkpoint_freq, exploit_freq}, ENV{width, height, max_num_cities, max_rails_between_cities, max_rail_pairs_in_city,
 number_of_agents, malfunction_rate, min_duration, max_duration}, MODEL{gamma, epsilon, epsilon_decay_rate, lr,
-lr_decay_rate, default_q, num_episodes}.  Two optional keys are new: ENV.fixture (a map fixture .npz recorded from
-flatland, see tools/record_flatland_fixture.py) and MISC.n_envs (lockstep replicas with seeds random_seed + i).
+lr_decay_rate, default_q, num_episodes}.  Three optional keys are new: ENV.fixture (a map fixture .npz recorded from
+flatland, see tools/record_flatland_fixture.py), MISC.n_envs (lockstep replicas with seeds random_seed + i) and
+MISC.q_cap (Q hash rows per environment; default: sized from the map, see ``default_q_cap``).
 Without ENV.fixture the map comes from the synthetic generator with the same size / train count / seed, because
 flatland's sparse_rail_generator cannot run here (mapgen.py).
 """
@@ -38,9 +39,20 @@ def fixture_from_env_section(env: Dict[str, str], seed: int) -> dict:
     return mapgen.make_fixture(n=n, n_trains=int(env["number_of_agents"]), n_chords=chords, seed=seed, num_cities=cities)
 
 
-def launch_experiment(config_path: str, device: str = "cuda:0", _engine_kwargs=None) -> DistrQLearning:
+def default_device() -> str:
+    """``cuda:<LOCAL_RANK>`` (one process per GPU under torchrun), made current for torch."""
+    import torch
+    local = sharding.world()[2]
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return f"cuda:{local}"
+
+
+def launch_experiment(config_path: str, device: Optional[str] = None, q_cap: Optional[int] = None, env_cls=ASyncSwitchEnv,
+                      _engine_kwargs=None) -> DistrQLearning:
     """main.py:13-78."""
     start_time = time.time()
+    device = device or default_device()
     config = configparser.ConfigParser()
     config.read(config_path)
     misc, envs, mdl = config["MISC"], config["ENV"], config["MODEL"]
@@ -49,8 +61,10 @@ def launch_experiment(config_path: str, device: str = "cuda:0", _engine_kwargs=N
     mf = ParamMalfunctionGen(MalfunctionParameters(malfunction_rate=float(envs["malfunction_rate"]),
                                                    min_duration=int(envs["min_duration"]), max_duration=int(envs["max_duration"])))
     rail_env = RailEnv(fixture_from_env_section(dict(envs), seed), malfunction_generator=mf)
-    env = ASyncSwitchEnv(rail_env, render_mode=None, max_steps=100_000, n_envs=int(misc.get("n_envs", 1)), device=device,
-                         _engine_kwargs=_engine_kwargs)
+    if q_cap is None and misc.get("q_cap"):
+        q_cap = int(misc["q_cap"])
+    env = env_cls(rail_env, render_mode=None, max_steps=100_000, n_envs=int(misc.get("n_envs", 1)), device=device, q_cap=q_cap,
+                  _engine_kwargs=_engine_kwargs)
     model = DistrQLearning(env=env, gamma=float(mdl["gamma"]), epsilon=float(mdl["epsilon"]),
                            epsilon_decay_rate=float(mdl["epsilon_decay_rate"]), lr=float(mdl["lr"]),
                            lr_decay_rate=float(mdl["lr_decay_rate"]), default_q=float(mdl["default_q"]), seed=seed)
@@ -74,13 +88,14 @@ def launch_experiment(config_path: str, device: str = "cuda:0", _engine_kwargs=N
 
 def launch_grid(hyperparams: Dict[str, Sequence[float]], random_seeds: Sequence[int], out_dir: str, env_section: Dict[str, object],
                 num_episodes: int, checkpoint_freq: int, exploit_freq: Optional[int], gamma: float = 1.0, default_q: float = 0.0,
-                device: str = "cuda:0", _engine_kwargs=None) -> List[str]:
+                device: Optional[str] = None, q_cap: Optional[int] = None, env_cls=ASyncSwitchEnv, _engine_kwargs=None) -> List[str]:
     """hyperparam_tuning.py:42-91: every (grid point, seed) pair gets ``out_dir/exp_i/seed_j/`` with its config.ini
     and the reference's output files.  One seed = one map (the generators are seeded with it), so each seed is ONE
     batched engine whose environments are the grid points; under torchrun the seeds are sharded over the ranks."""
     names = list(hyperparams)
     points = [dict(zip(names, v)) for v in product(*[hyperparams[n] for n in names])]
     rank, world_size, _ = sharding.world()
+    device = device or default_device()
     lo, hi = sharding.shard_range(len(random_seeds), rank, world_size)
     written = []
     for rdx in range(lo, hi):
@@ -88,8 +103,8 @@ def launch_grid(hyperparams: Dict[str, Sequence[float]], random_seeds: Sequence[
         fx = fixture_from_env_section({k: str(v) for k, v in env_section.items()}, seed)
         mf = ParamMalfunctionGen(MalfunctionParameters(float(env_section.get("malfunction_rate", 0.0)),
                                                        int(env_section.get("min_duration", 0)), int(env_section.get("max_duration", 0))))
-        env = ASyncSwitchEnv(RailEnv(fx, malfunction_generator=mf), render_mode=None, max_steps=100_000, n_envs=len(points),
-                             device=device, _engine_kwargs=_engine_kwargs)
+        env = env_cls(RailEnv(fx, malfunction_generator=mf), render_mode=None, max_steps=100_000, n_envs=len(points),
+                      device=device, q_cap=q_cap, _engine_kwargs=_engine_kwargs)
         col = lambda k, d: np.array([p.get(k, d) for p in points], np.float64)
         model = DistrQLearning(env=env, gamma=gamma, epsilon=col("epsilon", 0.4), epsilon_decay_rate=col("epsilon_decay_rate", 0.0),
                                lr=col("lr", 0.4), lr_decay_rate=col("lr_decay_rate", 0.0), default_q=default_q,
@@ -112,12 +127,13 @@ def launch_grid(hyperparams: Dict[str, Sequence[float]], random_seeds: Sequence[
     return written
 
 
-def launch_eval(exp_dir_list: Sequence[str], distr_q_model_name: str = "distr_q_model.pkl", device: str = "cuda:0",
-                _engine_kwargs=None) -> Dict[str, np.ndarray]:
+def launch_eval(exp_dir_list: Sequence[str], distr_q_model_name: str = "distr_q_model.pkl", device: Optional[str] = None,
+                q_cap: Optional[int] = None, env_cls=ASyncSwitchEnv, _engine_kwargs=None) -> Dict[str, np.ndarray]:
     """eval.py:31-97: for every experiment directory reload ``config.ini`` + the pickled Q-table and run the greedy
     ``test()`` -- once, or ten times when the map has malfunctions (eval.py:88).  The evaluations are the environment
     axis of one engine (environment i draws its malfunctions from seed + i) and go to ``eval_i/`` like the reference's."""
     out = {}
+    device = device or default_device()
     for exp_dir in exp_dir_list:
         print(f"Evaluating {exp_dir}")
         config = configparser.ConfigParser()
@@ -126,8 +142,9 @@ def launch_eval(exp_dir_list: Sequence[str], distr_q_model_name: str = "distr_q_
         rate = float(envs["malfunction_rate"])
         mf = ParamMalfunctionGen(MalfunctionParameters(rate, int(envs["min_duration"]), int(envs["max_duration"])))
         num_evals = 10 if rate > 0 else 1
-        env = ASyncSwitchEnv(RailEnv(fixture_from_env_section(dict(envs), seed), malfunction_generator=mf), render_mode=None,
-                             max_steps=100_000, n_envs=num_evals, device=device, _engine_kwargs=_engine_kwargs)
+        cap = q_cap if q_cap is not None else (int(config["MISC"]["q_cap"]) if config["MISC"].get("q_cap") else None)
+        env = env_cls(RailEnv(fixture_from_env_section(dict(envs), seed), malfunction_generator=mf), render_mode=None,
+                      max_steps=100_000, n_envs=num_evals, device=device, q_cap=cap, _engine_kwargs=_engine_kwargs)
         model = DistrQLearning(env=env, gamma=float(mdl["gamma"]), epsilon=float(mdl["epsilon"]),
                                epsilon_decay_rate=float(mdl["epsilon_decay_rate"]), lr=float(mdl["lr"]),
                                lr_decay_rate=float(mdl["lr_decay_rate"]), default_q=float(mdl["default_q"]), seed=seed)
@@ -147,9 +164,10 @@ def launch_eval(exp_dir_list: Sequence[str], distr_q_model_name: str = "distr_q_
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("-c", "--config", type=str, help="Config file path", required=True)
-    ap.add_argument("--device", default="cuda:0")
+    ap.add_argument("--device", default=None, help="default: cuda:<LOCAL_RANK>")
+    ap.add_argument("--q-cap", type=int, default=None, help="Q hash rows per environment (default: MISC.q_cap, else sized from the map)")
     args = ap.parse_args(argv)
-    launch_experiment(args.config, device=args.device)
+    launch_experiment(args.config, device=args.device, q_cap=args.q_cap)
 
 
 if __name__ == "__main__":

@@ -937,7 +937,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g
         case ST_WAITING: if (in_malf) nxt = ST_MALF_OFF; else if (ed_reached) nxt = ST_READY; break;
         case ST_READY: if (in_malf) nxt = ST_MALF_OFF; else if (valid_move) nxt = ST_MOVING; break;
         case ST_MALF_OFF:
-          if (!in_malf) { if (ed_reached) nxt = valid_move ? ST_MOVING : (stop_given ? ST_STOPPED : ST_READY); else nxt = ST_WAITING; }
+          if (!in_malf) { if (ed_reached) nxt = valid_move ? ST_MOVING : ST_STOPPED; else nxt = ST_WAITING; }   // Appendix B step 4
           break;
         case ST_MOVING: if (in_malf) nxt = ST_MALF; else if (stop_given || conflict) nxt = ST_STOPPED; break;
         case ST_STOPPED: if (in_malf) nxt = ST_MALF; else if (valid_move) nxt = ST_MOVING; break;

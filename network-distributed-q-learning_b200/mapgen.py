@@ -267,6 +267,16 @@ def loop_chord_fixture() -> dict:
     }
 
 
+def offmap_malfunction_fixture() -> dict:
+    """The 7x7 loop + chord map with two trains that share their entry cell (opposite headings): with injected
+    malfunctions it exercises flatland's MALFUNCTION_OFF_MAP -> STOPPED transition onto an occupied cell (row F4)."""
+    fx = loop_chord_fixture()
+    fx.update(name="f4_offmap_7x7", init_pos=np.array([[2, 1], [2, 1]], np.int32), init_dir=np.array([0, 2], np.int32),
+              target=np.array([[3, 4], [1, 2]], np.int32), earliest_departure=np.array([0, 2], np.int32),
+              latest_arrival=np.array([30, 40], np.int32), max_episode_steps=80)
+    return fx
+
+
 _SCALARS = ("max_episode_steps", "malfunction_rate", "min_duration", "max_duration")
 
 

@@ -17,7 +17,7 @@ Executes the reference's OWN ``switchfl`` code, unmodified, from /root/reference
 Outputs go to tests/golden/<fixture>.npz (+ the fixture itself as <fixture>.fixture.npz).  The GPU box
 never runs this file: it has no /root/reference.
 
-    python oracle/gen_golden.py            # regenerate every golden
+    python oracle/gen_golden.py [name ...]   # regenerate every golden (or the named ones)
 """
 from __future__ import annotations
 
@@ -45,8 +45,13 @@ HPARAMS = dict(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_dec
 
 
 def fixtures():
+    """(fixture, seed, episodes, hyper-parameters[, injected malfunctions {(tick, train): duration}])."""
     fx = mapgen.loop_chord_fixture()
     yield fx, 450565, 3, dict(HPARAMS)
+    # Row F4, SURVEY Appendix B step 4 "MALF_OFF_MAP -> (done & ed) STOPPED": train 1 breaks down before departing; when its
+    # counter runs out (tick 6, past its earliest departure) its entry cell is occupied by train 0, which broke down ON
+    # that cell -- no valid movement, so train 1 goes STOPPED and is placed on the occupied cell.
+    yield (mapgen.offmap_malfunction_fixture(), 450565, 2, dict(HPARAMS), {(3, 0): 12, (1, 1): 5})
     # C1-synthetic: test_model.py:14-63 parameters on the synthetic generator
     yield (mapgen.make_fixture(18, 2, 4, seed=450565 % 1000, num_cities=5, malfunction_rate=0.01, min_duration=5,
                                max_duration=15, name="c1_synth18"), 450565, 5, dict(HPARAMS))
@@ -70,7 +75,7 @@ def _load_vendored_distance_map():
     return mod
 
 
-def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, verbose=True):
+def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, inject=None, verbose=True):
     import logging
     logging.disable(logging.INFO)
     from switchfl.distr_q import DistrQLearning
@@ -78,6 +83,8 @@ def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, verbose=True):
     from switchfl.utils.naming import name2switch_id
 
     rail_env = trainsim.RailEnv(fx)
+    if inject is not None:
+        rail_env.injected_malfunctions = dict(inject)         # the same schedule in every episode (replay input)
     env = ASyncSwitchEnv(rail_env, render_mode=None, max_steps=100_000)
     rn = env.rail_network
     out = {}
@@ -257,6 +264,8 @@ def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, verbose=True):
     out["ep_delays"] = np.asarray(ep_del, np.float64).reshape(n_episodes, T)
     out["ep_num_malfunctions"] = np.asarray(ep_mal, np.int32)
     out["seed"] = np.int64(seed)
+    if inject is not None:                                    # free-running consumers must inject the same schedule
+        out["inject_events"] = np.array([(t, h, d) for (t, h), d in sorted(inject.items())], np.int32).reshape(-1, 3)
     out["n_episodes"] = np.int32(n_episodes)
     for k, v in hp.items():
         out["hp_" + k] = np.float64(v)
@@ -268,9 +277,17 @@ def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, verbose=True):
 
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    for fx, seed, n_ep, hp in fixtures():
+    only = set(sys.argv[1:])
+    for fx, seed, n_ep, hp, *rest in fixtures():
+        if only and fx["name"] not in only:
+            continue
         mapgen.check_fixture(fx)
-        out = run_fixture(fx, seed, n_ep, hp)
+        out = run_fixture(fx, seed, n_ep, hp, inject=rest[0] if rest else None)
+        if fx["name"] == "f4_offmap_7x7":                     # the transition under test is really taken
+            st = out["tick_state"][:, 1]
+            assert any(a == 2 and b == 4 for a, b in zip(st[:-1], st[1:])), "MALFUNCTION_OFF_MAP -> STOPPED not taken"
+            k = int(np.nonzero((st[:-1] == 2) & (st[1:] == 4))[0][0]) + 1
+            assert out["tick_pos"][k, 0] == out["tick_pos"][k, 1] >= 0, "train 1 was not placed on the occupied entry cell"
         mapgen.save_fixture(os.path.join(GOLDEN_DIR, fx["name"] + ".fixture.npz"), fx)
         np.savez_compressed(os.path.join(GOLDEN_DIR, fx["name"] + ".npz"), **out)
 

@@ -537,14 +537,12 @@ class RailEnv:
                 elif valid_move:
                     nxt = TrainState.MOVING
             elif st == TrainState.MALFUNCTION_OFF_MAP:
+                # MALF_OFF_MAP -> (done & ed & valid) MOVING | (done & ed) STOPPED |
+                # (done & not ed) WAITING.  A train whose entry cell is occupied when its off-map malfunction ends
+                # therefore goes STOPPED -- an on-map state, so it is placed on its initial cell (position update below)
                 if counter_complete:
                     if ed_reached:
-                        if valid_move:
-                            nxt = TrainState.MOVING
-                        elif stop_given:
-                            nxt = TrainState.STOPPED
-                        else:
-                            nxt = TrainState.READY_TO_DEPART
+                        nxt = TrainState.MOVING if valid_move else TrainState.STOPPED
                     else:
                         nxt = TrainState.WAITING
             elif st == TrainState.MOVING:

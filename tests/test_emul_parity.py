@@ -8,17 +8,7 @@ from switchfl_b200 import backend
 from tests._parity import check_replay
 from tests._util import golden_names
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = os.path.join(ROOT, "network-distributed-q-learning_b200", "csrc")
-EMUL = os.path.join(ROOT, "tests", "emul", "libsfl_emul.so")
-
-
-def build_emul():
-    srcs = [os.path.join(SRC, f) for f in ("sfl_api.cu", "sfl_core.cuh")] + [os.path.join(ROOT, "include", "switchfl_b200.h")]
-    if not os.path.exists(EMUL) or any(os.path.getmtime(s) > os.path.getmtime(EMUL) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-DSFL_HOST_EMUL", "-x", "c++",
-                               "-I", os.path.join(ROOT, "include"), "-I", SRC, "-o", EMUL, os.path.join(SRC, "sfl_api.cu")])
-    return EMUL
+from tests.emulated import EmulEngine, EmulSwitchEnv, build_emul, emul_distance_map  # noqa: F401
 
 
 @pytest.fixture(scope="session")
@@ -28,11 +18,11 @@ def emul_lib():
 
 @pytest.mark.parametrize("name", golden_names())
 def test_emul_replay_matches_reference(name, emul_lib):
-    check_replay(name, lambda rm, **kw: backend.Engine(rm, _emul_lib=emul_lib, **kw), n_envs=2)
+    check_replay(name, EmulEngine, n_envs=2)
 
 
 def test_emul_chunked_launches_equal_one_launch(emul_lib):
-    check_replay("slips24_t6", lambda rm, **kw: backend.Engine(rm, _emul_lib=emul_lib, **kw), n_envs=1, chunk=7)
+    check_replay("slips24_t6", EmulEngine, n_envs=1, chunk=7)
 
 
 def test_emul_abandons_episode_exactly_where_the_reference_raises(emul_lib):
@@ -47,7 +37,7 @@ def test_emul_abandons_episode_exactly_where_the_reference_raises(emul_lib):
     rm = backend.RailMap(fx)
     hp = dict(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0)
     B, n_ep, T = 8, 6, 50
-    eng = backend.Engine(rm, n_envs=B, q_cap=16384, dec_cap=60000, tick_cap=5000, ep_cap=8, _emul_lib=emul_lib)
+    eng = EmulEngine(rm, n_envs=B, q_cap=16384, dec_cap=60000, tick_cap=5000, ep_cap=8)
     eng.set_hparams(**hp, seeds=np.arange(B) + 450565, episodes=n_ep)
     eng.reset()
     eng.enable_q_init(True)
@@ -90,8 +80,8 @@ def _aec_env(name, emul_lib, n_envs=1):
     from tests._util import load_golden
     fx, g = load_golden(name)
     ev = golden_events(g)
-    env = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=n_envs, q_cap=64, ep_cap=2,
-                             _engine_kwargs={"_emul_lib": emul_lib, "ev_cap": len(ev) + 2})
+    env = EmulSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=n_envs, q_cap=64, ep_cap=2,
+                        _engine_kwargs={"ev_cap": len(ev) + 2})
     env.engine.set_replay(None, [ev] * n_envs)
     return env, g
 
@@ -189,7 +179,7 @@ def test_emul_truncation_by_max_steps(emul_lib):
     from tests._parity import check_against_oracle
     from tests._util import load_golden
     fx, _ = load_golden("slips24_t6")
-    check_against_oracle(lambda rm, **kw: backend.Engine(rm, _emul_lib=emul_lib, **kw), fx, HP_EDGE, 3, [5, 6], max_steps=25)
+    check_against_oracle(EmulEngine, fx, HP_EDGE, 3, [5, 6], max_steps=25)
 
 
 def test_emul_greedy_rollout_after_training(emul_lib):
@@ -197,13 +187,13 @@ def test_emul_greedy_rollout_after_training(emul_lib):
     from tests._parity import check_against_oracle
     from tests._util import load_golden
     fx, _ = load_golden("slips24_t6")
-    check_against_oracle(lambda rm, **kw: backend.Engine(rm, _emul_lib=emul_lib, **kw), fx, HP_EDGE, 2, [11, 12], greedy_after=True)
+    check_against_oracle(EmulEngine, fx, HP_EDGE, 2, [11, 12], greedy_after=True)
 
 
 @pytest.mark.parametrize("kind", ["one_train", "max_trains"])
 def test_emul_train_count_extremes(kind, emul_lib):
     from tests._parity import check_against_oracle
-    check_against_oracle(lambda rm, **kw: backend.Engine(rm, _emul_lib=emul_lib, **kw), edge_fixture(kind), HP_EDGE, 1, [21, 22],
+    check_against_oracle(EmulEngine, edge_fixture(kind), HP_EDGE, 1, [21, 22],
                          q_cap=65536 if kind == "max_trains" else 1024)
 
 
@@ -230,7 +220,7 @@ def test_emul_fuzz_maps_against_oracle(i, emul_lib):
         fx, hp, seeds, max_steps = fuzz_case(i)
     except ValueError as ex:                                    # "map too small for the requested number of trains"
         pytest.skip(str(ex))
-    check_against_oracle(lambda rm, **kw: backend.Engine(rm, _emul_lib=emul_lib, **kw), fx, hp, 3, seeds, max_steps=max_steps,
+    check_against_oracle(EmulEngine, fx, hp, 3, seeds, max_steps=max_steps,
                          greedy_after=True, q_cap=16384)
 
 
@@ -242,7 +232,7 @@ def test_emul_distance_map_matches_vendored_reference(name, emul_lib):
     from tests._util import load_golden
     fx, g = load_golden(name)
     rm = backend.RailMap(fx)
-    d = backend.device_distance_map(fx["grid"], rm.trains.targets, _emul_lib=emul_lib)
+    d = emul_distance_map(fx["grid"], rm.trains.targets)
     assert np.array_equal(d, rm.trains.dist)
     assert np.array_equal(d[rm.trains.tgt_index], g["dist"])                 # golden: one map per train handle
 
@@ -255,7 +245,7 @@ def test_emul_malfunction_draws_have_the_flatland_distribution(emul_lib):
     fx, _ = load_golden("c1_synth18")                                     # rate 0.01, durations 5..15
     rm = backend.RailMap(fx)
     B, T = 8192, 2
-    eng = backend.Engine(rm, n_envs=B, q_cap=64, ep_cap=2, tick_cap=60, _emul_lib=emul_lib)
+    eng = EmulEngine(rm, n_envs=B, q_cap=64, ep_cap=2, tick_cap=60)
     eng.set_hparams(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0,
                     seeds=np.arange(B) * 7919 + 5, episodes=1)
     eng.reset()

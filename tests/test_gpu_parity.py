@@ -346,15 +346,14 @@ def test_cuda_production_kernels_equal_the_full_kernel(name, lanes):
 def test_cuda_free_running_learn_equals_the_host_build(name):
     """Free-running learn (Philox epsilon-greedy and malfunction draws included) on the device against the same sources
     compiled for the host (tests/emul): identical counters, episode logs and Q-tables for identical seeds."""
-    from tests.test_emul_parity import build_emul
-    emul = build_emul()
+    from tests.emulated import EmulEngine
     fx, _ = load_golden(name)
     rm = backend.RailMap(fx)
     hp = dict(gamma=0.95, epsilon=0.5, epsilon_decay_rate=0.999, lr=0.2, lr_decay_rate=1.0, default_q=0.0)
     B, n_ep = 12, 4
     out = []
-    for kw in (dict(device="cuda:0"), dict(_emul_lib=emul)):
-        eng = backend.Engine(rm, n_envs=B, q_cap=4096, ep_cap=8, **kw)
+    for cls in (backend.Engine, EmulEngine):
+        eng = cls(rm, n_envs=B, q_cap=4096, ep_cap=8)
         eng.set_hparams(**hp, seeds=np.arange(B) + 31, episodes=n_ep)
         eng.reset()
         eng.enable_q_init(True)

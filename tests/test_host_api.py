@@ -16,7 +16,7 @@ import pytest
 import __graft_entry__ as entry
 from switchfl_b200 import api, backend, mapgen, sharding
 from tests._util import load_golden
-from tests.test_emul_parity import build_emul
+from tests.emulated import EmulEngine, EmulSwitchEnv, build_emul
 
 ROOT = entry.ROOT
 HEADER = os.path.join(ROOT, "include", "switchfl_b200.h")
@@ -111,7 +111,7 @@ def test_drop_in_learn_outputs_have_the_reference_layout():
     emul = build_emul()
     fx, _ = load_golden("c1_synth18")
     rail_env = api.RailEnv(fx, malfunction_generator=api.ParamMalfunctionGen(api.MalfunctionParameters(0.01, 5, 15)))
-    env = api.ASyncSwitchEnv(rail_env, render_mode=None, max_steps=100_000, n_envs=3, q_cap=1024, ep_cap=4, _engine_kwargs={"_emul_lib": emul})
+    env = EmulSwitchEnv(rail_env, render_mode=None, max_steps=100_000, n_envs=3, q_cap=1024, ep_cap=4)
     assert env.possible_agents == env.rail_map.tab.switch_names()
     model = api.DistrQLearning(env=env, gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0, seed=450565)
     with tempfile.TemporaryDirectory() as out:
@@ -166,6 +166,7 @@ from __graft_entry__ import load_package
 load_package()
 import torch.distributed as dist
 from switchfl_b200 import backend, mapgen, sharding
+from tests.emulated import EmulEngine
 rank, ws, _ = sharding.world()
 dist.init_process_group("gloo", rank=rank, world_size=ws)
 fx = mapgen.load_fixture(os.path.join(sys.argv[1], "tests", "golden", "c1_synth18.fixture.npz"))
@@ -173,7 +174,7 @@ rm = backend.RailMap(fx)
 grid = sharding.grid_points({"epsilon": [0.5, 0.2], "lr": [0.1]}, seeds=[64, 65, 66])
 mine = sharding.shard_grid(grid, rank, ws)
 n = len(mine["seeds"])
-eng = backend.Engine(rm, n_envs=n, q_cap=1024, ep_cap=4, _emul_lib=sys.argv[2])
+eng = EmulEngine(rm, n_envs=n, q_cap=1024, ep_cap=4)
 eng.set_hparams(gamma=1.0, epsilon=mine["epsilon"], epsilon_decay_rate=0.9997, lr=mine["lr"], lr_decay_rate=1.0, default_q=0.0,
                 seeds=mine["seeds"], episodes=3)
 eng.reset(); eng.enable_q_init(True)
@@ -195,7 +196,7 @@ def test_two_ranks_shard_the_grid_and_reduce_like_one_process():
     fx, _ = load_golden("c1_synth18")
     rm = backend.RailMap(fx)
     grid = sharding.grid_points({"epsilon": [0.5, 0.2], "lr": [0.1]}, seeds=[64, 65, 66])
-    eng = backend.Engine(rm, n_envs=6, q_cap=1024, ep_cap=4, _emul_lib=emul)
+    eng = EmulEngine(rm, n_envs=6, q_cap=1024, ep_cap=4)
     eng.set_hparams(gamma=1.0, epsilon=grid["epsilon"], epsilon_decay_rate=0.9997, lr=grid["lr"], lr_decay_rate=1.0, default_q=0.0,
                     seeds=grid["seeds"], episodes=3)
     eng.reset(); eng.enable_q_init(True)
@@ -236,7 +237,7 @@ def test_cli_runs_the_reference_ini(capsys):
     with tempfile.TemporaryDirectory() as tmp:
         ini = os.path.join(tmp, "config.ini")
         _write_ini(ini, os.path.join(tmp, "out"), fixture=os.path.join(ROOT, "tests", "golden", "c1_synth18.fixture.npz"))
-        model = cli.launch_experiment(ini, _engine_kwargs={"_emul_lib": emul})
+        model = cli.launch_experiment(ini, env_cls=EmulSwitchEnv)
         out = capsys.readouterr().out
         for line in ("DONE!", "TOTAL TIME:", "Seconds per episode:", "Flatland step time:", "Total step time:", "Total last time:",
                      "Action selection time:", "Update time:", "Flatland reset time:", "Total reset time:"):          # main.py:68-78
@@ -245,7 +246,7 @@ def test_cli_runs_the_reference_ini(capsys):
         assert model.metrics["cum_reward"].shape == (2, 4)
         # without ENV.fixture the synthetic generator builds a map of the requested size / train count
         _write_ini(ini, os.path.join(tmp, "out2"))
-        m2 = cli.launch_experiment(ini, _engine_kwargs={"_emul_lib": emul})
+        m2 = cli.launch_experiment(ini, env_cls=EmulSwitchEnv)
         assert m2.env.rail_env.width == 18 and m2.env.rail_env.get_num_agents() == 2
 
 
@@ -259,9 +260,9 @@ def test_grid_launcher_writes_the_reference_tree():
     with tempfile.TemporaryDirectory() as tmp:
         dirs = cli.launch_grid({"epsilon": [0.5, 0.1], "epsilon_decay_rate": [0.9997], "lr": [0.1], "lr_decay_rate": [1.0]},
                                random_seeds=[64, 65], out_dir=tmp, env_section=env_section, num_episodes=3, checkpoint_freq=10 ** 9,
-                               exploit_freq=None, _engine_kwargs={"_emul_lib": emul})
+                               exploit_freq=None, env_cls=EmulSwitchEnv)
         assert sorted(os.path.relpath(d, tmp) for d in dirs) == ["exp_0/seed_0", "exp_0/seed_1", "exp_1/seed_0", "exp_1/seed_1"]
-        res = cli.launch_eval(dirs[:2], _engine_kwargs={"_emul_lib": emul})                       # eval.py:31-97
+        res = cli.launch_eval(dirs[:2], env_cls=EmulSwitchEnv)                       # eval.py:31-97
         for d in dirs[:2]:
             assert res[d].shape == (2, 1) and np.load(os.path.join(d, "eval_0", "cum_reward.npz"))["x"].shape == ()
             assert len(np.load(os.path.join(d, "eval_0", "delays.npz"))["x"]) == 2
@@ -278,7 +279,7 @@ HP_SHARED = dict(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_d
 
 
 def _shared_run(rm, emul, seeds, launches=5, ticks=64, dist=None):
-    eng = backend.Engine(rm, n_envs=len(seeds), q_cap=2, ep_cap=4, shared_q=True, _emul_lib=emul)
+    eng = EmulEngine(rm, n_envs=len(seeds), q_cap=2, ep_cap=4, shared_q=True)
     eng.set_hparams(**HP_SHARED, seeds=seeds, episodes=-1)
     eng.reset()
     eng.init_shared_q(0.0)
@@ -303,7 +304,7 @@ def test_shared_table_mode_is_deterministic_and_averages():
     mixed = _shared_run(rm, emul, [1, 2, 3, 4, 5, 6])
     qm = mixed.shared_q_table()
     assert np.isfinite(qm).all() and not np.array_equal(qm, q1)
-    init = backend.Engine(rm, n_envs=1, q_cap=2, shared_q=True, _emul_lib=emul)
+    init = EmulEngine(rm, n_envs=1, q_cap=2, shared_q=True)
     init.init_shared_q(0.0)
     q0 = init.shared_q_table()
     assert set(np.unique(q0)) <= {0.0, 500.0, 1000.0} and (q0 == 500.0).any()             # distr_q.py:44-45, 156-181

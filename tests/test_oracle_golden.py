@@ -13,6 +13,8 @@ def test_oracle_matches_reference_trace(name):
     fx, g = load_golden(name)
     tab = ref_tables(fx, g)
     o = SwitchFLOracle(fx, tab, seed=int(g["seed"]), **hparams(g))
+    if "inject_events" in g:                                  # goldens recorded with an injected malfunction schedule
+        o.rail_env.injected_malfunctions = {(int(t), int(h)): int(d) for t, h, d in g["inject_events"]}
     o.enable_trace()
     eps = o.learn(int(g["n_episodes"]))
     t = o.trace
@@ -55,3 +57,14 @@ def test_oracle_replay_equals_free_run(name):
     assert np.array_equal(np.array(o.trace["tick_malf"], np.int32).reshape(g["tick_malf"].shape), g["tick_malf"])
     assert np.array_equal(np.array(o.trace["dec_reward"]), g["dec_reward"])
     assert o.q_table == q_dict(g["q_keys"], g["q_vals"])
+
+
+def test_f4_golden_takes_the_off_map_malfunction_to_stopped_transition():
+    """Row F4: MALFUNCTION_OFF_MAP -> STOPPED when the counter runs out past the earliest
+    departure and no valid movement is possible; the train is placed on its (occupied) entry cell."""
+    _, g = load_golden("f4_offmap_7x7")
+    st, pos = g["tick_state"], g["tick_pos"]
+    k = np.nonzero((st[:-1, 1] == 2) & (st[1:, 1] == 4))[0]
+    assert len(k), "transition not in the trace"
+    k = int(k[0]) + 1
+    assert pos[k, 1] == pos[k, 0] >= 0 and st[k, 0] == 5      # on train 0's cell, which is broken down there
