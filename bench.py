@@ -42,10 +42,10 @@ WORKLOADS = {
            "C3: hyperparam_tuning.py default grid (eps .5, decay .9997, lr .1) x seeds {64,65,66,67,69} = 5 maps (80x80, 15 trains, "
            "25 cities, no malfunctions; synthetic stand-ins), each (map, point) replicated with distinct RNG streams: "
            "5 x 4096 envs per GPU, distributed Q-learning, learn mode"),
-    "c4": ("c4_synth100_t50", 8192, 65536,
-           "C4: large synthetic map (100x100, 50 trains, 281 switches, malfunctions), 65536 envs per 8 GPUs = 8192 per GPU, "
+    "c4": ("c4_rail100_t50", 8192, 65536,
+           "C4: large synthetic map (100x100, 50 trains, 354 switches, malfunctions), 65536 envs per 8 GPUs = 8192 per GPU, "
            "distributed Q-learning, learn mode"),
-    "c5": ("c4_synth100_t50", 8192, 2,
+    "c5": ("c4_rail100_t50", 8192, 2,
            "C5 (extension, no reference counterpart): the C4 map in shared-table mode -- all 8192 envs of a GPU read one dense "
            "Q table and accumulate TD steps; every step (512 ticks) the integer accumulators are all-reduced over the GPUs "
            "(NCCL) and the mean step is folded into the table"),
@@ -72,8 +72,7 @@ def workload_fixtures():
     """The maps of the selected workload: one for C2 / C4, the five seed maps of the hyper-parameter grid for C3."""
     from switchfl_b200 import mapgen
     if FIXTURE == "@c3":                                                  # hyperparam_tuning.py:17-26, synthetic stand-ins
-        return [mapgen.make_fixture(n=80, n_trains=15, n_chords=50, seed=s, num_cities=25, name=f"c3_synth80_s{s}", p_slip=0.3)
-                for s in C3_SEEDS]
+        return [mapgen.c3_fixture(s) for s in C3_SEEDS]
     return [mapgen.load_fixture(FIXTURE)]
 
 

@@ -61,17 +61,30 @@ class _Builder:
         self._add(r, c, _opp(h_out), _opp(h_in))
         self.kind[(r, c)] = "curve"
 
-    def loop(self, r0, c0, r1, c1):
-        for c in range(c0 + 1, c1):
-            self.straight(r0, c, 1)      # top row heading E
-            self.straight(r1, c, 3)      # bottom row heading W
-        for r in range(r0 + 1, r1):
-            self.straight(r, c1, 2)      # right column heading S
-            self.straight(r, c0, 0)      # left column heading N
-        self.curve(r0, c0, 0, 1)
-        self.curve(r0, c1, 1, 2)
-        self.curve(r1, c1, 2, 3)
-        self.curve(r1, c0, 3, 0)
+    def loop(self, r0, c0, r1, c1, reverse=False):
+        """rectangular loop; the clockwise world runs it clockwise -- or counter-clockwise when ``reverse``."""
+        if not reverse:
+            for c in range(c0 + 1, c1):
+                self.straight(r0, c, 1)      # top row heading E
+                self.straight(r1, c, 3)      # bottom row heading W
+            for r in range(r0 + 1, r1):
+                self.straight(r, c1, 2)      # right column heading S
+                self.straight(r, c0, 0)      # left column heading N
+            self.curve(r0, c0, 0, 1)
+            self.curve(r0, c1, 1, 2)
+            self.curve(r1, c1, 2, 3)
+            self.curve(r1, c0, 3, 0)
+        else:
+            for c in range(c0 + 1, c1):
+                self.straight(r0, c, 3)
+                self.straight(r1, c, 1)
+            for r in range(r0 + 1, r1):
+                self.straight(r, c1, 0)
+                self.straight(r, c0, 2)
+            self.curve(r0, c0, 3, 2)
+            self.curve(r0, c1, 0, 3)
+            self.curve(r1, c1, 1, 0)
+            self.curve(r1, c0, 2, 1)
 
     def try_chord(self, p: Tuple[int, int], q: Tuple[int, int], rng) -> bool:
         """straight chord between p and q (same row or same column, at least one cell between)."""
@@ -167,6 +180,102 @@ def generate_grid(n: int, n_chords: int, seed: int, margin: int = 1, allow_cross
     return b.grid.astype(np.uint16)
 
 
+def generate_grid_v2(n: int, seed: int, n_rings: int = 2, ring_gap: int = 2, cross_every: int = 14, n_lines: int = 6,
+                     double_lines: bool = True, p_slip: float = 0.2, margin: int = 1, with_headings: bool = False):
+    """Double-track layout (stand-in for flatland's sparse_rail_generator with max_rails_between_cities = 2,
+    hyperparam_tuning.py:17-26): ``n_rings`` concentric main-line loops ``ring_gap`` cells apart, joined by crossovers
+    roughly every ``cross_every`` cells in alternating orientation, and ``n_lines`` interior lines across the innermost
+    ring -- each a PAIR of parallel tracks two cells apart when ``double_lines`` -- so that opposing trains can pass
+    each other instead of meeting head-on on a single track.  Built from the same two primitives as ``generate_grid``
+    (loop + straight chord), so the strong-connectivity argument of the module docstring carries over: every ring is
+    strongly connected in both worlds, and a chord only adds a path between two nodes of a strongly connected digraph
+    (crossovers are added in both orientations between every pair of neighbouring rings).
+
+    Right-hand running: in the clockwise world neighbouring rings run in OPPOSITE senses and the two tracks of a line
+    pair in opposite directions, so that world alone reaches every place in both directions of travel on separate
+    tracks -- a double-track railway under its normal operating rule.  ``with_headings`` also returns int8[n, n], the
+    clockwise-world heading on every plain straight cell (-1 elsewhere), for ``make_fixture(headings=...)``: trains
+    started with those headings all follow the rule; trains started against them run wrong-way and meet the others
+    head-on, as on the single-track maps of ``generate_grid``."""
+    rng = np.random.RandomState(seed)
+    b = _Builder(n)
+    rings = []
+    for k in range(n_rings):
+        m = margin + ring_gap * k
+        if n - 1 - m - m < 6:
+            break
+        b.loop(m, m, n - 1 - m, n - 1 - m, reverse=bool(k % 2))
+        rings.append(m)
+    # ---- crossovers between neighbouring rings (alternating orientation, on all four sides)
+    for k in range(len(rings) - 1):
+        mo, mi = rings[k], rings[k + 1]
+        lo, hi = mi + 2, n - 1 - mi - 2                       # keep clear of the corners of the inner ring
+        flip = k % 2
+        for side in range(4):
+            pos = lo + int(rng.randint(0, max(cross_every // 2, 1)))
+            while pos <= hi:
+                if side == 0: p, q = (mo, pos), (mi, pos)                          # top
+                elif side == 1: p, q = (pos, n - 1 - mo), (pos, n - 1 - mi)        # right
+                elif side == 2: p, q = (n - 1 - mo, pos), (n - 1 - mi, pos)        # bottom
+                else: p, q = (pos, mo), (pos, mi)                                  # left
+                ends = (p, q) if flip else (q, p)
+                if b.try_chord(ends[0], ends[1], rng):
+                    flip ^= 1
+                    pos += max(3, cross_every + int(rng.randint(-cross_every // 4, cross_every // 4 + 1)))
+                else:
+                    pos += 1
+    # ---- interior lines across the innermost ring
+    mi = rings[-1]
+    added, tries = 0, 0
+    while added < n_lines and tries < 400 * max(n_lines, 1):
+        tries += 1
+        vertical = bool(rng.randint(2))
+        pos = int(rng.randint(mi + 3, n - 1 - mi - 4))
+        if vertical: p, q, off = (mi, pos), (n - 1 - mi, pos), (0, 2)
+        else: p, q, off = (pos, mi), (pos, n - 1 - mi), (2, 0)
+        if rng.rand() < 0.5:
+            p, q = q, p
+        # a line may stop at the first earlier line it meets instead of crossing everything
+        if rng.rand() < 0.5:
+            d = (2 if q[0] > p[0] else 0) if vertical else (1 if q[1] > p[1] else 3)
+            r, c = p[0] + DR[d], p[1] + DC[d]
+            steps = 1
+            while (r, c) != q:
+                k_ = b.kind.get((r, c))
+                axis = 0 if vertical else 1
+                if k_ == "straight" and (1 - axis) in b.cw[(r, c)] and steps >= 4 and rng.rand() < 0.4:
+                    q = (r, c)
+                    break
+                r, c = r + DR[d], c + DC[d]
+                steps += 1
+        p2, q2 = (p[0] + off[0], p[1] + off[1]), (q[0] + off[0], q[1] + off[1])
+        snap = (b.grid.copy(), {k_: dict(v) for k_, v in b.cw.items()}, dict(b.kind))
+        if not b.try_chord(p, q, rng):
+            continue
+        if double_lines and not b.try_chord(q2, p2, rng):      # the second track of the pair runs the other way
+            b.grid, b.cw, b.kind = snap                      # keep lines double: undo the first track
+            continue
+        added += 1
+    if p_slip > 0:
+        for cell in sorted(c for c, k in b.kind.items() if k == "cross"):
+            if rng.rand() >= p_slip:
+                continue
+            hv, hh = b.cw[cell][0], b.cw[cell][1]
+            first = (hh, hv) if rng.rand() < 0.5 else (hv, hh)
+            pairs = [first] if rng.rand() < 0.5 else [first, (first[1], first[0])]
+            for (a, z) in pairs:
+                b._add(cell[0], cell[1], a, z)
+                b._add(cell[0], cell[1], _opp(z), _opp(a))
+    grid = b.grid.astype(np.uint16)
+    if not with_headings:
+        return grid
+    heads = np.full((n, n), -1, np.int8)
+    for (r, c), k in b.kind.items():
+        if k == "straight":
+            heads[r, c] = next(iter(b.cw[(r, c)].values()))
+    return grid, heads
+
+
 def plain_cells(grid: np.ndarray) -> List[Tuple[int, int, int, int]]:
     """(r, c, heading_a, heading_b) for straight, non-crossing, non-switch track cells."""
     out = []
@@ -183,8 +292,14 @@ def plain_cells(grid: np.ndarray) -> List[Tuple[int, int, int, int]]:
 
 def make_fixture(n: int = 18, n_trains: int = 2, n_chords: int = 4, seed: int = 0, num_cities: int = 2,
                  malfunction_rate: float = 0.0, min_duration: int = 0, max_duration: int = 0,
-                 name: Optional[str] = None, p_slip: float = 0.0) -> dict:
-    grid = generate_grid(n, n_chords, seed, p_slip=p_slip)
+                 name: Optional[str] = None, p_slip: float = 0.0, grid: Optional[np.ndarray] = None, slack: float = 1.0,
+                 headings: Optional[np.ndarray] = None, wrong_way: float = 0.0) -> dict:
+    """``grid``: a ready transition grid (e.g. ``generate_grid_v2``) instead of the loop + chords generator;
+    ``slack`` stretches the episode length and the arrival windows of the timetable; ``headings`` (from
+    ``generate_grid_v2(with_headings=True)``): start every train with the right-hand-running heading of its cell, except
+    a fraction ``wrong_way`` started against it."""
+    if grid is None:
+        grid = generate_grid(n, n_chords, seed, p_slip=p_slip)
     rng = np.random.RandomState(seed + 7919)
     cells = plain_cells(grid)
     # keep starts/targets away from switches so that _init_ports always walks at least one cell
@@ -202,7 +317,12 @@ def make_fixture(n: int = 18, n_trains: int = 2, n_chords: int = 4, seed: int = 
     tgts = [cells[i] for i in order[n_trains:2 * n_trains]]
     trains = []
     for (sr, sc, ha, hb), (tr, tc, _, _) in zip(starts, tgts):
-        trains.append(((sr, sc), int((ha, hb)[rng.randint(2)]), (tr, tc)))
+        d0 = int((ha, hb)[rng.randint(2)])
+        if headings is not None and headings[sr, sc] >= 0:
+            d0 = int(headings[sr, sc])
+            if rng.rand() < wrong_way:
+                d0 = _opp(d0)
+        trains.append(((sr, sc), d0, (tr, tc)))
     trains.sort(key=lambda t: t[0] + (t[1],))          # switch_env.py:104-119 ordering
     # ---- timetable (flatland_patch/timetable_generators.py:23-136, speed 1.0, single-leg lines)
     lens = []
@@ -215,7 +335,7 @@ def make_fixture(n: int = 18, n_trains: int = 2, n_chords: int = 4, seed: int = 
     max_steps_old = int(4 * 2 * (n + n + (n_trains / num_cities)))
     mean_delay = float(np.mean(times)) * 0.2
     max_steps_new = int(np.ceil(float(np.max(times)) * 1.5) + mean_delay)
-    max_episode_steps = min(max_steps_new, int(max_steps_old * 3.0))
+    max_episode_steps = int(min(max_steps_new, int(max_steps_old * 3.0)) * slack)
     end_buffer = int(max_episode_steps * 0.05)
     la_max = max_episode_steps - end_buffer
     eds, las = [], []
@@ -265,6 +385,29 @@ def loop_chord_fixture() -> dict:
         "max_episode_steps": 60,
         "malfunction_rate": 0.0, "min_duration": 0, "max_duration": 0,
     }
+
+
+def rail_fixture(n: int, n_trains: int, seed: int, n_rings: int = 2, n_lines: int = 8, cross_every: int = 10, p_slip: float = 0.2,
+                 num_cities: int = 25, malfunction_rate: float = 0.0, min_duration: int = 0, max_duration: int = 0,
+                 wrong_way: float = 0.0, name: Optional[str] = None) -> dict:
+    """A double-track map (``generate_grid_v2``) with a right-hand-running timetable: the stand-in for flatland's
+    ``sparse_rail_generator(max_rails_between_cities=2)`` + ``sparse_line_generator`` (main.py:36-49,
+    hyperparam_tuning.py:17-26) that the C3 / C4 benchmark configurations and their goldens use."""
+    grid, heads = generate_grid_v2(n, seed, n_rings=n_rings, n_lines=n_lines, cross_every=cross_every, p_slip=p_slip, with_headings=True)
+    return make_fixture(n, n_trains, 0, seed=seed, num_cities=num_cities, malfunction_rate=malfunction_rate, min_duration=min_duration,
+                        max_duration=max_duration, name=name or f"rail{n}_t{n_trains}_s{seed}", grid=grid, headings=heads,
+                        wrong_way=wrong_way)
+
+
+def c3_fixture(seed: int) -> dict:
+    """BASELINE.json configs[2]: hyperparam_tuning.py:10-35 -- 80x80, 15 trains, 25 cities, rails 2/2, no malfunctions."""
+    return rail_fixture(80, 15, seed, n_rings=2, n_lines=8, cross_every=10, num_cities=25, name=f"c3_rail80_s{seed}")
+
+
+def c4_fixture() -> dict:
+    """BASELINE.json configs[3]: large synthetic map -- 100x100, 50 trains, hundreds of switches, malfunctions 0.01 / 5-15."""
+    return rail_fixture(100, 50, 0, n_rings=3, n_lines=20, cross_every=8, num_cities=25, malfunction_rate=0.01, min_duration=5,
+                        max_duration=15, name="c4_rail100_t50")
 
 
 def offmap_malfunction_fixture() -> dict:

@@ -60,7 +60,10 @@ def fixtures():
            dict(HPARAMS, lr_decay_rate=0.9999, gamma=0.95, default_q=1.5))
     yield (mapgen.make_fixture(40, 12, 30, seed=5, num_cities=4, malfunction_rate=0.0, name="synth40_t12",
                                p_slip=0.3), 65, 2, dict(HPARAMS))
-    # C3-class: BASELINE.json configs[2] -- hyperparam_tuning.py:10-35 (80x80, 15 trains, 25 cities, no malfunctions), seed 64
+    # C3 / C4: BASELINE.json configs[2] / configs[3] on the double-track generator -- the maps bench.py times
+    yield (mapgen.c3_fixture(64), 64, 3, dict(HPARAMS))
+    yield (mapgen.c4_fixture(), 7, 3, dict(HPARAMS))
+    # Congested single-track maps of the same classes (edge cases: gridlock, forced stops, the reference's crash site)
     yield (mapgen.make_fixture(n=80, n_trains=15, n_chords=50, seed=64, num_cities=25, name="c3_synth80_s64", p_slip=0.3),
            64, 2, dict(HPARAMS))
     # C4-class: BASELINE.json configs[3] -- 100x100, 50 trains (T > 32: both mask words), 281 switches, malfunctions
