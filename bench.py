@@ -4,16 +4,18 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, one rank per GPU under torchrun)
     python bench.py --impl reference [...]                         the reference's CPU path (oracle port, all host cores)
 
-Workload (N = 1): BASELINE.json configs[1] -- 4096 lockstep environments of the test_model.py map
-(18x18, 2 trains, malfunction rate 0.01 / 5-15, gamma 1, eps .5 decay .9997, lr .1; synthetic-map stand-in
-``c1_synth18`` because flatland's generators are unavailable) learning with distributed Q-learning.  One
-"step" = one launch of the hot-path kernel advancing every environment by ``--ticks`` flatland ticks plus
-every switch-agent decision, Q-update and episode reset in between.  N > 1: the same per GPU (weak scaling),
-environments sharded by seed range, no data-path collective.
+Headline workload: BASELINE.json configs[3], the configuration the north-star target is quoted on -- the large synthetic map
+(100x100, 50 trains, 354 switches, malfunctions 0.01 / 5-15; ``c4_rail100_t50``) with 8192 lockstep environments per GPU
+(65536 on 8), every environment an independent distributed-Q learner (gamma 1, eps .5 decay .9997, lr .1).  One "step" =
+one launch of the hot-path kernel advancing every environment by ``--ticks`` flatland ticks plus every switch-agent
+decision, Q-update and episode reset in between.  N > 1: the same per GPU (weak scaling), environments sharded by seed
+range, no data-path collective.  The other configurations (C2 = configs[1], C3 = configs[2],
+C5 = configs[4]) are measured in the same run and reported under ``extra``.
 
-Prints ONE JSON line (rank 0).  value = device-timed (CUDA events, max over ranks) decisions/s with all
-state resident in HBM; e2e = the same through the public Python API (DistrQLearning.learn_chunk) with the
-per-env hyper-parameter block copied host->device and the per-env counters copied device->host every step.
+Prints ONE JSON line (rank 0).  value = device-timed (CUDA events on the launch stream, max over ranks) decisions/s with
+all state resident in HBM; e2e = the same metric through the public drop-in API the reference's scripts call --
+``DistrQLearning.learn(num_episodes, ...)`` (main.py:63) -- wall clock, with the per-env hyper-parameter block copied
+host->device and the per-env counters / episode logs copied device->host inside the timed region.
 """
 from __future__ import annotations
 
@@ -34,46 +36,38 @@ from __graft_entry__ import load_package  # noqa: E402
 METRIC = "switch_agent_decisions_per_sec"
 HP = dict(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0)   # test_model.py:56-63
 SEED = 450565
-# workload -> (fixture, envs per GPU, Q hash rows per env, description)
+C3_SEEDS = (64, 65, 66, 67, 69)                                          # hyperparam_tuning.py:10
+# workload -> (fixture, envs per GPU, Q hash rows per env, description); "@c3" = the five seed maps of the hyper-parameter grid
 WORKLOADS = {
     "c2": ("c1_synth18", 4096, 1024,
-           "C2: 4096 lockstep envs of the test_model.py map (c1_synth18 stand-in), distributed Q-learning, learn mode"),
+           "C2: 4096 lockstep envs of the test_model.py map (18x18, 2 trains, malfunctions; c1_synth18 stand-in), distributed Q-learning, learn mode"),
     "c3": ("@c3", 20480, 32768,
            "C3: hyperparam_tuning.py default grid (eps .5, decay .9997, lr .1) x seeds {64,65,66,67,69} = 5 maps (80x80, 15 trains, "
-           "25 cities, no malfunctions; synthetic stand-ins), each (map, point) replicated with distinct RNG streams: "
+           "25 cities, double track, no malfunctions; synthetic stand-ins), each (map, point) replicated with distinct RNG streams: "
            "5 x 4096 envs per GPU, distributed Q-learning, learn mode"),
     "c4": ("c4_rail100_t50", 8192, 65536,
-           "C4: large synthetic map (100x100, 50 trains, 354 switches, malfunctions), 65536 envs per 8 GPUs = 8192 per GPU, "
-           "distributed Q-learning, learn mode"),
+           "C4: large synthetic map (100x100, 50 trains, 354 switches, double track, malfunctions 0.01 / 5-15), 65536 envs per "
+           "8 GPUs = 8192 per GPU, distributed Q-learning, learn mode"),
     "c5": ("c4_rail100_t50", 8192, 2,
            "C5 (extension, no reference counterpart): the C4 map in shared-table mode -- all 8192 envs of a GPU read one dense "
-           "Q table and accumulate TD steps; every step (512 ticks) the integer accumulators are all-reduced over the GPUs "
-           "(NCCL) and the mean step is folded into the table"),
+           "Q table and accumulate TD steps; every step the integer accumulators are all-reduced over the GPUs (NCCL) and the "
+           "mean step is folded into the table"),
 }
-SHARED_Q = False
-FIXTURE = os.path.join(ROOT, "tests", "golden", "c1_synth18.fixture.npz")
-WORKLOAD = WORKLOADS["c2"][3]
+TICKS = {"c2": 8192, "c3": 1024, "c4": 1024, "c5": 1024}                 # flatland ticks per env per step (launch)
+FIXTURE = None                                                            # set in main (the CPU workers re-derive the maps from it)
 
 
-def select_workload(args):
-    global FIXTURE, WORKLOAD, SHARED_Q
-    name, envs, q_cap, desc = WORKLOADS[args.workload]
-    SHARED_Q = args.workload == "c5"
-    FIXTURE = name if name.startswith("@") else os.path.join(ROOT, "tests", "golden", name + ".fixture.npz")
-    WORKLOAD = desc if not args.envs or args.envs == envs else desc + f" [envs per GPU overridden: {args.envs}]"
-    args.envs = args.envs or envs
-    args.q_cap = args.q_cap or q_cap
+def fixture_path(name):
+    return name if name.startswith("@") else os.path.join(ROOT, "tests", "golden", name + ".fixture.npz")
 
 
-C3_SEEDS = (64, 65, 66, 67, 69)                                          # hyperparam_tuning.py:10
-
-
-def workload_fixtures():
-    """The maps of the selected workload: one for C2 / C4, the five seed maps of the hyper-parameter grid for C3."""
+def workload_fixtures(fixture=None):
+    """The maps of a workload: one for C2 / C4 / C5, the five seed maps of the hyper-parameter grid for C3."""
     from switchfl_b200 import mapgen
-    if FIXTURE == "@c3":                                                  # hyperparam_tuning.py:17-26, synthetic stand-ins
+    fixture = fixture or FIXTURE
+    if fixture == "@c3":                                                  # hyperparam_tuning.py:17-26, synthetic stand-ins
         return [mapgen.c3_fixture(s) for s in C3_SEEDS]
-    return [mapgen.load_fixture(FIXTURE)]
+    return [mapgen.load_fixture(fixture)]
 
 
 def bytes_per_decision(k_bar: float, P: float, A: float, A2: float) -> float:
@@ -83,8 +77,8 @@ def bytes_per_decision(k_bar: float, P: float, A: float, A2: float) -> float:
 
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi sampled every 20 ms from before the warm-up until the end of the e2e arm; the median SM clock is taken
-    over the samples that fall inside the device-timed region when there are any, else over all samples under load."""
+    """nvidia-smi sampled every 20 ms for the whole run; the median SM clock is taken over the samples that fall inside
+    the device-timed region of the headline workload."""
     Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -123,15 +117,18 @@ class ClockSampler:
             except ValueError:
                 continue
             sm.append(clk); mx.append(cmax)
+            inside = False
             try:
                 ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                if self.window and self.window[0] <= ts <= self.window[1]:
-                    sm_in.append(clk)
+                inside = bool(self.window and self.window[0] <= ts <= self.window[1])
             except ValueError:
                 pass
-            for n, v in zip(names, parts[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+            if inside:
+                sm_in.append(clk)
+            if inside or not self.window:
+                for n, v in zip(names, parts[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
         os.unlink(self.f.name)
         if sm:
             use = sm_in if sm_in else sm
@@ -143,22 +140,24 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------- CPU arm
 def _cpu_worker(args):
     seed, budget_s, n_ep, fixture = args
-    global FIXTURE
-    FIXTURE = fixture
     load_package()
-    from switchfl_b200 import backend, mapgen
+    from switchfl_b200 import backend
     from oracle.switchfl_oracle import SwitchFLOracle
-    fxs = workload_fixtures()
+    fxs = workload_fixtures(fixture)
     fx = fxs[seed % len(fxs)]
     rm = backend.RailMap(fx)
     o = SwitchFLOracle(fx, rm.tab, seed=seed, **HP)
     rng = np.random.default_rng(seed)
     o.episode = 0
     t0 = time.perf_counter()
-    dec = 0
-    eps = 0
+    dec = eps = 0
     while True:
-        m = o.run_episode(rng, greedy=False, learn=True)
+        try:
+            m = o.run_episode(rng, greedy=False, learn=True)
+        except RuntimeError as ex:                         # the reference dies here too (observer.py:294-307): the run ends
+            if "No train detected" not in str(ex):
+                raise
+            break
         dec += m["decisions"]
         eps += 1
         if (n_ep and eps >= n_ep) or (not n_ep and time.perf_counter() - t0 >= budget_s):
@@ -180,13 +179,19 @@ def cpu_sample(budget_s: float, cores: int, n_ep: int = 0, seed0: int = SEED):
     return dec, busy, wall, sum(r[2] for r in res)
 
 
+CPU_NOTE = ("CPU oracle port of the reference path (the reference itself needs flatland, absent here); measured in the build container on "
+            "one process, the port is 2-7x FASTER than the reference's own switchfl code on the same flatland shim (C1: 1307 vs 180, "
+            "C3: 2495 vs 1284 decisions/s, identical decision counts), and the shim is lighter than real flatland: ratios against "
+            "this arm are conservative")
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step_s = 1.0
-    for _ in range(args.warmup):
+    per_step_s = 2.0
+    for _ in range(min(args.warmup, 1)):
         cpu_sample(per_step_s, cores)
     dec, busy = 0, 0.0
     for _ in range(args.steps):
@@ -194,12 +199,12 @@ def run_reference_arm(args):
         dec += d
         busy += b
     value = dec / busy
-    sample = f"{cores} processes x {per_step_s:.0f} s of oracle learn() episodes per step on {os.path.basename(FIXTURE)}, one seed per process"
+    sample = (f"{cores} processes x about {per_step_s:.0f} s of oracle learn() episodes per step on {os.path.basename(FIXTURE)}, one seed per "
+              f"process (hyperparam_tuning.py:85-91); whole episodes, so a step can run over")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * busy / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_envs": cores, "note": "CPU oracle port of the reference path (reference itself needs flatland, absent); "
-                       "its flatland substrate is lighter than real flatland, so this arm is faster than the true reference"},
+            "config": {"workload": WORKLOADS[args.workload][3], "n_envs": cores, "note": CPU_NOTE},
             "cpu_baseline": {"value": value, "unit": "decisions/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -207,75 +212,112 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------- our arm
-def run_ours(args):
-    import torch
-    load_package()
-    from switchfl_b200 import api, backend, mapgen
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    dev = f"cuda:{local}"
-    fxs = workload_fixtures()
-    B = args.envs
+class Ctx:
+    """torch / torch.distributed handles of this rank."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        self.dev = f"cuda:{self.local}"
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device(self.dev))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, times, counts):
+        """MAX of the timings, SUM of the work counters over the ranks."""
+        if self.dist is None:
+            return [float(x) for x in times], [int(x) for x in counts]
+        t = self.torch.tensor(list(times), device=self.dev, dtype=self.torch.float64)
+        c = self.torch.tensor(list(counts), device=self.dev, dtype=self.torch.int64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        self.dist.all_reduce(c, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()], [int(x) for x in c.tolist()]
+
+
+def kernel_counters(workload):
+    """Per-launch ncu counters of the workload's k_run (committed under profiles/, NOT measured by this run)."""
+    path = os.path.join(ROOT, "profiles", "kernel_counters.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get(workload)
+    return None
+
+
+def run_block(cx: Ctx, wl: str, args, steps: int, warmup: int, sampler=None, flush_l2="auto") -> dict:
+    """Device-resident arm of one workload: Engine level, CUDA-event timed, one engine per map."""
+    torch = cx.torch
+    from switchfl_b200 import backend
+    fixture, envs, q_cap, desc = WORKLOADS[wl]
+    shared = wl == "c5"
+    head = wl == args.workload
+    ticks = (args.ticks if head else 0) or TICKS[wl]
+    fxs = workload_fixtures(fixture_path(fixture))
+    B = (args.envs if (args.envs and head) else envs)
+    q_cap = args.q_cap if (args.q_cap and head) else q_cap
     parts = len(fxs)
     Bp = B // parts                                                       # environments per map
     B = Bp * parts
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+    kw = {"lanes": args.lanes or None, "cta_warps": args.cta_warps or None} if head else {}
 
     def seeds_of(k):
-        return np.arange(Bp, dtype=np.uint64) + np.uint64(SEED + rank * B + k * Bp)
+        return np.arange(Bp, dtype=np.uint64) + np.uint64(SEED + cx.rank * B + k * Bp)
 
-    # ---------------- device-resident arm: Engine level, CUDA-event timed (one engine per map, one stream)
     rms = [backend.RailMap(fx) for fx in fxs]
-    engs = [backend.Engine(rm, n_envs=Bp, device=dev, q_cap=args.q_cap, ep_cap=4, lanes=args.lanes or None, shared_q=SHARED_Q,
-                           cta_warps=args.cta_warps or None) for rm in rms]
-    lanes = engs[0].lanes
+    engs = [backend.Engine(rm, n_envs=Bp, device=cx.dev, q_cap=q_cap, ep_cap=4, shared_q=shared, **kw) for rm in rms]
     for k, eng in enumerate(engs):
         eng.set_hparams(**HP, seeds=seeds_of(k), episodes=-1)
         eng.reset()
         eng.enable_q_init(True)
-        if SHARED_Q:
+        if shared:
             eng.init_shared_q(HP["default_q"])
+    sync_ev = []
 
-    def launch(eng):
-        eng.run(backend.MODE_LEARN, args.ticks)
-        if SHARED_Q:
-            eng.shared_q_sync(dist)                                       # all-reduce of the accumulators + apply kernel
+    def launch(eng, timed=False):
+        eng.run(backend.MODE_LEARN, ticks)
+        if shared:
+            if timed:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            eng.shared_q_sync(cx.dist)                                    # all-reduce of the accumulators + apply kernel
+            if timed:
+                b.record()
+                sync_ev.append((a, b))
 
     # Timing hygiene: the env state + Q tables are larger than L2, but on the small map the lines a launch actually touches
     # are not (ncu: 11 MB of DRAM traffic per launch), so L2 is flushed between the timed steps (256 MB written); the
     # flush sits inside the bracketed region, i.e. `value` pays for it.  Large-map workloads touch GBs per launch.
     state_bytes = sum(eng.sizes.state_bytes for eng in engs)
     flush = None
-    if args.flush_l2 == "on" or (args.flush_l2 == "auto" and state_bytes < (1 << 30)):
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(args.warmup):
+    if flush_l2 == "on" or (flush_l2 == "auto" and state_bytes < (1 << 30)):
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=cx.dev)
+    for _ in range(warmup):
         for eng in engs:
             launch(eng)
-    barrier()
+    cx.barrier()
 
     def totals():
-        d = t = tt = 0
+        out = np.zeros(8, np.int64)
         for eng in engs:
-            a, b_ = eng.total_decisions()
-            d += a; t += b_; tt += int(eng.counters()["train_ticks"].sum())
-        return d, t, tt
+            c = eng.counters()
+            out += [int(c[k].sum()) for k in ("decisions", "ticks", "train_ticks", "episodes", "aborted", "forced_stops", "stop_actions",
+                                              "arrived_trains")]
+        return out
 
-    d0, t0, tt0 = totals()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    t0 = totals()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    cx.barrier()
     wall0 = time.time()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
@@ -284,126 +326,183 @@ def run_ours(args):
             flush.zero_()
         a.record()
         for eng in engs:
-            launch(eng)
+            launch(eng, timed=True)
         b.record()
     stop.record()
-    barrier()
+    cx.barrier()
     if sampler:
         sampler.mark(wall0, time.time())
     ms = start.elapsed_time(stop)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs])) / parts            # mean duration of ONE k_run launch
-    d1, t1, tt1 = totals()
-    episodes = aborted = q_rows_max = 0
-    state_mb = 0.0
+    step_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    sync_ms = float(np.mean([a.elapsed_time(b) for a, b in sync_ev])) if sync_ev else 0.0
+    kern_ms = (step_ms - sync_ms * parts) / parts                         # mean duration of ONE k_run launch
+    t1 = totals()
+    q_rows_max, state_mb = 0, 0.0
+    variant = engs[0].describe_launch(backend.MODE_LEARN)
+    lanes = engs[0].lanes
+    shared_cells = engs[0]._shared_cells() if shared else 0
     for eng in engs:
         # On congested maps the reference itself dies in observer.py:294-307 ("No train detected at active switch");
         # the kernel abandons such an episode and resets the env.  Every other error bit is fatal here.
         eng.check_errors(allow=backend.ERR_NO_TRAIN_AT_SWITCH)
-        cn = eng.counters()
-        episodes += int(cn["episodes"].sum()); aborted += int(cn["aborted"].sum())
-        q_rows_max = max(q_rows_max, int(cn["q_rows"].max()))
+        q_rows_max = max(q_rows_max, int(eng.counters()["q_rows"].max()))
         state_mb += eng.sizes.state_bytes / 1e6
         eng.close()
-    dec, ticks, train_ticks = d1 - d0, t1 - t0, tt1 - tt0
-    del engs
+    flushed = flush is not None
+    del engs, flush
     torch.cuda.empty_cache()
-
-    # ---------------- end-to-end arm: public API, host buffers in the timed region
-    models = []
-    for k, fx in enumerate(fxs):
-        env = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=Bp, device=dev, q_cap=args.q_cap, ep_cap=4,
-                                 shared_q=SHARED_Q, _engine_kwargs={"lanes": args.lanes or None, "cta_warps": args.cta_warps or None})
-        models.append(api.DistrQLearning(env=env, seeds=seeds_of(k), dist=dist, **HP))
-    for _ in range(args.warmup):
-        for m in models:
-            m.learn_chunk(args.ticks)
-    barrier()
-    c0 = sum(int(m.learn_chunk(0)["decisions"].sum()) for m in models)
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(args.steps):
-        cs = [m.learn_chunk(args.ticks) for m in models]
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0
-    e2e_dec = sum(int(c["decisions"].sum()) for c in cs) - c0
-    clocks = sampler.stop() if sampler else None
-    h2d = sum(int(m.env.engine.sizes.hparams_bytes) for m in models)
-    d2h = sum(int(m.env.engine.sizes.counters_bytes) for m in models)
-
-    # ---------------- reduce over ranks: max time, summed work
-    if dist is not None:
-        t = torch.tensor([ms, e2e_s, kern_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        w = torch.tensor([dec, ticks, train_ticks, e2e_dec], device=dev, dtype=torch.int64)
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        ms, e2e_s, kern_ms = (float(x) for x in t.tolist())
-        dec, ticks, train_ticks, e2e_dec = (int(x) for x in w.tolist())
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-    value = dec / (ms / 1000.0)
+    (ms, kern_ms, sync_ms), d = cx.reduce([ms, kern_ms, sync_ms], list(t1 - t0))
+    dec, n_ticks, train_ticks, episodes, aborted, forced, stops, arrived = d
+    T = int(rms[0].trains.T)
     k_bar = train_ticks / max(dec, 1)
     P = float(np.mean(np.concatenate([rm.tab.sw_P for rm in rms]))); A = float(np.mean(np.concatenate([rm.tab.sw_A for rm in rms])))
     bpd = bytes_per_decision(k_bar, P, A, A)
+    dec_per_launch = dec / cx.world / steps / parts                       # per GPU
+    out = {"workload": desc, "value": dec / (ms / 1000.0), "unit": "decisions/s", "ms_per_step": ms / steps, "timed_region_s": ms / 1000.0,
+           "steps": steps, "warmup": warmup, "ticks_per_step": ticks, "n_envs_per_gpu": B, "maps": parts, "q_cap": q_cap, "lanes_per_env": lanes,
+           "kernel": variant, "kernel_ms": kern_ms, "decisions_per_launch": dec_per_launch, "train_ticks_per_decision": k_bar,
+           "bytes_per_decision": bpd, "ticks": n_ticks,
+           "episodes": episodes, "arrived_trains_per_episode": arrived / max(episodes, 1), "trains": T,
+           "forced_stop_share": forced / max(dec, 1), "stop_action_share": stops / max(dec, 1),
+           "abandoned_episode_share": aborted / max(episodes, 1), "q_rows_max": q_rows_max,
+           "l2": (f"L2 flushed between the timed steps (256 MB written, inside the timed region); env state + Q tables {state_mb:.0f} MB per GPU"
+                  if flushed else
+                  f"inputs larger than L2: {state_mb:.0f} MB of env state + Q tables per GPU vs 126 MB L2, GBs touched per launch"),
+           "gpu_launches": steps * parts * (2 if shared else 1)}
+    if shared:
+        out["collective"] = {"op": "all_reduce(sum) of int64 step sums + int32 step counts, then sfl_shared_q_apply",
+                             "backend": "nccl" if cx.world > 1 else "none (1 GPU)", "bytes_per_step": shared_cells * 12,
+                             "ms_per_step": sync_ms, "share_of_step": sync_ms * parts / max(step_ms, 1e-9)}
+    return out
+
+
+def run_e2e(cx: Ctx, wl: str, args, ticks: int, episodes: int) -> dict:
+    """End-to-end arm: the call the reference's scripts make -- DistrQLearning.learn(num_episodes, ...) (main.py:63) -- per map,
+    wall clock, host<->device copies (hyper-parameter block up; counters, episode logs down) inside the timed region."""
+    torch = cx.torch
+    from switchfl_b200 import api
+    fixture, envs, q_cap, _ = WORKLOADS[wl]
+    fxs = workload_fixtures(fixture_path(fixture))
+    B = args.envs or envs
+    Bp = B // len(fxs)
+    B = Bp * len(fxs)
+    q_cap = args.q_cap or q_cap
+    models = []
+    for k, fx in enumerate(fxs):
+        env = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=Bp, device=cx.dev, q_cap=q_cap, ep_cap=max(episodes, 2),
+                                 shared_q=(wl == "c5"), _engine_kwargs={"lanes": args.lanes or None, "cta_warps": args.cta_warps or None})
+        m = api.DistrQLearning(env=env, seeds=np.arange(Bp, dtype=np.uint64) + np.uint64(SEED + cx.rank * B + k * Bp), dist=cx.dist, **HP)
+        m.ticks_per_launch = ticks
+        models.append(m)
+    for m in models:                                                      # warm-up: one short learn() (allocations, first launches)
+        m.learn(num_episodes=1, out_dir=None, checkpoint_freq=0)
+    for m in models:
+        m.env.engine.reset_io_counters()
+        m.total_decisions = 0
+    cx.barrier()
+    w0 = time.perf_counter()
+    for m in models:
+        m.learn(num_episodes=episodes, out_dir=None, checkpoint_freq=0)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    dec = sum(m.total_decisions for m in models)
+    launches = sum(m.env.engine.n_launches for m in models)
+    h2d = sum(m.env.engine.h2d_bytes for m in models)
+    d2h = sum(m.env.engine.d2h_bytes for m in models)
+    for m in models:
+        m.env.engine.close()
+    del models
+    torch.cuda.empty_cache()
+    (e2e_s,), (dec,) = cx.reduce([e2e_s], [dec])
+    return {"value": dec / e2e_s, "unit": "decisions/s", "h2d_bytes_per_step": h2d // max(launches, 1), "d2h_bytes_per_step": d2h // max(launches, 1),
+            "api": f"DistrQLearning.learn(num_episodes={episodes}, out_dir=None, checkpoint_freq=0) per map", "wall_s": e2e_s,
+            "launches": launches, "step": f"one k_run launch of {ticks} ticks; bytes are the totals copied inside learn() divided by its launches"}
+
+
+def run_ours(args):
+    load_package()
+    cx = Ctx()
+    wl = args.workload
+    ticks = args.ticks or TICKS[wl]
+    sampler = ClockSampler(cx.local) if cx.rank == 0 else None
+    main = run_block(cx, wl, args, args.steps, args.warmup, sampler=sampler, flush_l2=args.flush_l2)
+    clocks = sampler.stop() if sampler else None
+    # e2e: about as many flatland ticks per env as the device-resident arm ran
+    fx0 = workload_fixtures(fixture_path(WORKLOADS[wl][0]))[0]
+    ep = args.e2e_episodes or max(2, int(0.8 * args.steps * ticks / int(fx0["max_episode_steps"])))
+    e2e = run_e2e(cx, wl, args, ticks, ep)
+    extra = {}
+    for name in [x for x in args.extra.split(",") if x and x != wl]:
+        extra[name] = run_block(cx, name, args, max(3, args.steps // 2), max(3, args.warmup))
+    if cx.rank != 0:
+        if cx.dist is not None:
+            cx.dist.destroy_process_group()
+        return
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    per_gpu_dec_per_launch = dec / world / args.steps / parts
-    achieved = per_gpu_dec_per_launch * bpd / (kern_ms / 1000.0) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath)).get(args.workload, {})
-        if tj.get("ticks") == args.ticks and tj.get("envs") == B:
-            traffic = tj.get("dram_bytes_per_launch")
-    line = {"metric": METRIC, "value": value, "unit": "decisions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_envs_per_gpu": B, "maps": parts, "ticks_per_step": args.ticks, "q_cap": args.q_cap, "lanes_per_env": lanes,
-                       "train_ticks_per_decision": k_bar, "ticks": ticks, "episodes_rank0": episodes,
-                       "episodes_abandoned_rank0": aborted, "q_rows_max_rank0": q_rows_max,
-                       "l2": (f"L2 flushed between the timed steps (256 MB written, inside the timed region); env state + Q tables "
-                              f"{state_mb:.0f} MB per GPU" if flush is not None else
-                              f"inputs larger than L2: {state_mb:.0f} MB of env state + Q tables per GPU vs 126 MB L2, GBs touched per launch"),
-                       "sharding": ("envs by seed range; per step one integer all-reduce (sum) of the shared table's accumulators" if SHARED_Q
-                                    else "envs by seed range, no data-path collective")},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_run", "bytes_per_decision": bpd, "kernel_ms": kern_ms, "peak_source": peak_src,
-                         "note": "per-env decision chains are serial: latency/issue-bound, not HBM-bound (SURVEY 8d honest note)"},
-            "e2e": {"value": e2e_dec / e2e_s, "unit": "decisions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps * parts * (2 if SHARED_Q else 1), "clocks": clocks}
-    if world == 1 and not args.no_cpu:
+    achieved = main["decisions_per_launch"] * main["bytes_per_decision"] / (main["kernel_ms"] / 1000.0) / 1e9
+    kc = kernel_counters(wl) or {}
+    traffic = kc.get("dram_bytes_per_launch") if kc.get("ticks") == ticks and kc.get("envs") == main["n_envs_per_gpu"] else None
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": (kc.get("source", "") + " (committed ncu capture, NOT this run)") if traffic else None,
+            "kernel": main["kernel"], "bytes_per_decision": main["bytes_per_decision"], "kernel_ms": main["kernel_ms"], "peak_source": peak_src,
+            "note": "byte model of SURVEY 8d; the kernel keeps the env state in shared memory for the launch and is bound by "
+                    "instruction issue / dependent-load latency of the serial per-env decision chain, not by HBM (see `issue`)"}
+    if kc.get("warp_inst_per_decision"):
+        sm_hz = 1e6 * ((clocks or {}).get("sm_mhz") or 1965.0)
+        dps_gpu = main["value"] / cx.world
+        roof["issue"] = {"warp_inst_per_decision": kc["warp_inst_per_decision"], "threads_per_inst": kc.get("threads_per_inst"),
+                         "achieved_warp_inst_per_s": kc["warp_inst_per_decision"] * dps_gpu, "peak_warp_inst_per_s": 148 * 4 * sm_hz,
+                         "frac": kc["warp_inst_per_decision"] * dps_gpu / (148 * 4 * sm_hz),
+                         "source": kc.get("source", "") + " (committed ncu capture, NOT this run); peak = 148 SMs x 4 schedulers x SM clock"}
+    cfg = {k: main[k] for k in ("workload", "n_envs_per_gpu", "maps", "ticks_per_step", "q_cap", "lanes_per_env", "kernel",
+                                "train_ticks_per_decision", "ticks", "episodes", "trains", "arrived_trains_per_episode",
+                                "forced_stop_share", "stop_action_share", "abandoned_episode_share", "q_rows_max", "l2", "timed_region_s")}
+    cfg["sharding"] = ("envs by seed range, no data-path collective" if wl != "c5" else
+                       "envs by seed range; per step one integer all-reduce (sum) of the shared table's accumulators")
+    if "collective" in main:
+        cfg["collective"] = main["collective"]
+    line = {"metric": METRIC, "value": main["value"], "unit": "decisions/s", "n_gpus": cx.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": cfg, "roofline": roof, "e2e": e2e, "gpu_launches": main["gpu_launches"], "clocks": clocks,
+            "extra": extra}
+    if cx.world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         d, busy, wall, eps = cpu_sample(args.cpu_seconds, cores)
         line["cpu_baseline"] = {"value": d / busy, "unit": "decisions/s", "cores": cores, "kind": "port",
-                                "sample": f"{cores} processes x {args.cpu_seconds:.0f} s of oracle learn() episodes on the same map "
-                                          f"({eps} episodes, {d} decisions), one seed per process as hyperparam_tuning.py:85-91"}
+                                "sample": f"{cores} processes x about {args.cpu_seconds:.0f} s of oracle learn() episodes on the same map "
+                                          f"({eps} episodes, {d} decisions), one seed per process as hyperparam_tuning.py:85-91",
+                                "note": CPU_NOTE}
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    if cx.dist is not None:
+        cx.dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = BASELINE.json configs[1] (default), c4 = configs[3]")
-    ap.add_argument("--envs", type=int, default=0, help="environments per GPU (0 = the workload's own)")
-    ap.add_argument("--ticks", type=int, default=512, help="flatland ticks per env per step (launch)")
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS),
+                    help="headline workload: c4 = BASELINE.json configs[3] (default), c2 = configs[1], c3 = configs[2], c5 = configs[4]")
+    ap.add_argument("--extra", default="c2,c3,c5", help="comma list of further workloads measured in the same run (reported under `extra`)")
+    ap.add_argument("--envs", type=int, default=0, help="environments per GPU of the headline workload (0 = the workload's own)")
+    ap.add_argument("--ticks", type=int, default=0, help="flatland ticks per env per step of the headline workload (0 = its own: 1024, C2 8192)")
     ap.add_argument("--q-cap", type=int, default=0, help="Q hash rows per environment (0 = the workload's own)")
     ap.add_argument("--lanes", type=int, default=0, help="lanes of a warp per environment (0 = library default for the batch size)")
     ap.add_argument("--cta-warps", type=int, default=0, help="warps per CTA of the hot-path kernel (0 = library default)")
     ap.add_argument("--flush-l2", default="auto", choices=["auto", "on", "off"],
                     help="write 256 MB between the timed steps (auto: when the whole state is under 1 GiB)")
-    ap.add_argument("--cpu-seconds", type=float, default=3.0)
+    ap.add_argument("--e2e-episodes", type=int, default=0, help="episodes per env of the end-to-end learn() call (0 = about as many ticks as the timed steps)")
+    ap.add_argument("--cpu-seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    select_workload(args)
+    global FIXTURE
+    FIXTURE = fixture_path(WORKLOADS[args.workload][0])
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -9,9 +9,10 @@
  * bulk buffers are CALLER-OWNED device pointers (the Python host allocates them as torch tensors) and
  * the library never frees them; only the small map-constant block is owned by the context.  One
  * context per GPU per map, driven from one host thread; work is enqueued on the caller's stream
- * (a cudaStream_t passed as void*).  Several contexts (maps) may live in one process, but all of them must be driven on
- * ONE stream: the map / layout / launch constants of a launch sit in __constant__ memory, written in stream order just
- * before it.  There is no CPU path: without a CUDA device sfl_create fails.
+ * (a cudaStream_t passed as void*).  Several contexts (maps, devices) may live in one process and run on different streams at
+ * the same time: a launch carries its map / layout / arguments as kernel parameters, there is no process-global device
+ * state.  Every entry point runs on the device of its context and restores the caller's current device.  There is no CPU
+ * path: without a CUDA device sfl_create fails.
  */
 #ifndef SWITCHFL_B200_H
 #define SWITCHFL_B200_H
@@ -23,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SFL_ABI_VERSION 4
+#define SFL_ABI_VERSION 5
 
 enum {
   SFL_OK = 0,
@@ -135,6 +136,10 @@ typedef struct sfl_env_counters {      /* written by sfl_run for every env      
   int32_t episodes, err, q_rows, halted;
   int32_t n_dec_logged, n_tick_logged, n_ep_logged, elapsed;
   int32_t aborted, reserved;                /* episodes abandoned on SFL_ERR_NO_TRAIN_AT_SWITCH      */
+  uint64_t forced_stops;                    /* decisions whose action mask allowed STOP only (switch_agents.py:104-134)   */
+  uint64_t stop_actions;                    /* decisions that chose STOP                                                   */
+  uint64_t arrived_trains;                  /* trains at their destination, summed over the finished episodes (distr_q.py:364) */
+  uint64_t reserved2;
 } sfl_env_counters;
 
 typedef struct sfl_dec_rec {           /* one switch-agent decision (trace)                           */
@@ -171,6 +176,11 @@ typedef struct sfl_ep_rec {            /* one finished episode (distr_q.py:360-3
 int sfl_distance_map(const uint16_t *grid, int32_t H, int32_t W, const int32_t *target_cells, int32_t n_targets,
                      int32_t *dist, int device);
 
+/* Known-answer hook: the library's Q-update arithmetic -- distr_q.py:441-447, fp64, the
+ * reference's operator order, no FMA contraction -- evaluated ON THE DEVICE for n rows of host operands
+ * {q, lr, reward, gamma, max_next, bootstrap (0: the train stayed at the same switch, :444-447)}; out[i] = new Q(s, a). */
+int sfl_kat_q_update(const double *operands, int32_t n, double *out, int device);
+
 int sfl_abi_version(void);
 const char *sfl_last_error(void);
 
@@ -195,6 +205,15 @@ int sfl_get_lanes(void *ctx);
 /* Warps per CTA of the hot-path kernel: 0 = automatic (4, halved while the launch has fewer than 8 CTAs per SM), or 1, 2,
  * 4.  A scheduling choice only.                                                                        */
 int sfl_set_cta_warps(void *ctx, int warps);
+
+/* Compile-time variant of the large-map learn kernel: 1 = the one built for 4 CTAs per SM (more registers), 0 = the one
+ * for 7, -1 = automatic (roomy when the launch fits one wave anyway).  A scheduling choice only.                   */
+int sfl_set_roomy(void *ctx, int roomy);
+/* Which kernel instantiation and launch configuration sfl_run(mode) would use now (traced != 0: with decision / tick
+ * traces), as text: "k_run<G=..,KIND=..,TH=..,SQ=..,ONE=..,ROOMY=..> grid=.. block=.. smem=..".  No counterpart in the
+ * reference; it lets the parity tests name -- and force, with sfl_set_lanes / sfl_set_roomy -- exactly the
+ * instantiations the benchmark launches.  Needs no bound buffers.                                                  */
+int sfl_describe_launch(void *ctx, int mode, int traced, char *buf, int cap);
 
 /* enable the optimistic initialisation of distr_q.py:299-300 for rows created from now on           */
 int sfl_enable_q_init(void *ctx, int on);

@@ -18,6 +18,7 @@ from . import railmap
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libswitchfl_b200.so")
 
+ABI_VERSION = 5
 MODE_LEARN, MODE_GREEDY, MODE_REPLAY, MODE_STEP = 0, 1, 2, 3
 ERR_NO_TRAIN_AT_SWITCH = 1
 ERR_BITS = {1: "no train at active switch (observer.py:294-307)", 2: "infinite distance to target (observer.py:35-36)",
@@ -61,14 +62,15 @@ HPARAMS_DT = np.dtype([("gamma", "f8"), ("epsilon", "f8"), ("epsilon_decay_rate"
                        ("episodes", "i4"), ("episode_base", "i4"), ("malf_thr2", "u4")])
 COUNTERS_DT = np.dtype([("decisions", "u8"), ("ticks", "u8"), ("train_ticks", "u8"), ("episodes", "i4"), ("err", "i4"),
                         ("q_rows", "i4"), ("halted", "i4"), ("n_dec_logged", "i4"), ("n_tick_logged", "i4"),
-                        ("n_ep_logged", "i4"), ("elapsed", "i4"), ("aborted", "i4"), ("reserved", "i4")])
+                        ("n_ep_logged", "i4"), ("elapsed", "i4"), ("aborted", "i4"), ("reserved", "i4"),
+                        ("forced_stops", "u8"), ("stop_actions", "u8"), ("arrived_trains", "u8"), ("reserved2", "u8")])
 DEC_DT = np.dtype([("ep", "i4"), ("tick", "i4"), ("sw", "i4"), ("train", "i4"), ("key", "u4"), ("mask", "i4"), ("action", "i4"),
                    ("next_sw", "i4"), ("reward", "i4"), ("done", "i4"), ("arrived", "u8")])
 TICK_DT = np.dtype([("pos", "i4"), ("dir", "i1"), ("state", "i1"), ("malf", "i2")])
 STEP_DT = np.dtype([("pending", "i4"), ("sw", "i4"), ("train", "i4"), ("key", "u4"), ("mask", "i4"), ("done", "i4"), ("elapsed", "i4"),
                     ("last_next_sw", "i4"), ("arrived", "u8"), ("rewards", "i4", (64,))])
 EP_DT = np.dtype([("cum_reward", "f8"), ("decisions", "i4"), ("arrived", "i4"), ("num_malfunctions", "i4"), ("ticks", "i4"), ("arrived_mask", "u8")])
-assert HPARAMS_DT.itemsize == 80 and COUNTERS_DT.itemsize == 64 and DEC_DT.itemsize == 48 and TICK_DT.itemsize == 8 and EP_DT.itemsize == 32
+assert HPARAMS_DT.itemsize == 80 and COUNTERS_DT.itemsize == 96 and DEC_DT.itemsize == 48 and TICK_DT.itemsize == 8 and EP_DT.itemsize == 32
 
 
 def load_library(path: Optional[str] = None) -> C.CDLL:
@@ -87,13 +89,16 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sfl_set_lanes.argtypes = [C.c_void_p, C.c_int]
     lib.sfl_get_lanes.argtypes = [C.c_void_p]
     lib.sfl_set_cta_warps.argtypes = [C.c_void_p, C.c_int]
+    lib.sfl_set_roomy.argtypes = [C.c_void_p, C.c_int]
+    lib.sfl_describe_launch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int]
     lib.sfl_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.sfl_total_decisions.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
     lib.sfl_export_q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.c_void_p]
     lib.sfl_import_q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_int, C.c_void_p]
     lib.sfl_shared_q_apply.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sfl_kat_q_update.argtypes = [C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double), C.c_int]
     lib.sfl_distance_map.argtypes = [_u16p, C.c_int32, C.c_int32, _i32p, C.c_int32, _i32p, C.c_int]
-    if lib.sfl_abi_version() != 4:
+    if lib.sfl_abi_version() != ABI_VERSION:
         raise RuntimeError("switchfl_b200 ABI version mismatch")
     return lib
 
@@ -107,6 +112,17 @@ def device_distance_map(grid: np.ndarray, target_cells: Sequence[int], device: i
     H, W = g.shape
     out = np.empty((len(tg), H, W, 4), np.int32)
     rc = lib.sfl_distance_map(g.ctypes.data_as(_u16p), H, W, tg.ctypes.data_as(_i32p), len(tg), out.ctypes.data_as(_i32p), int(device))
+    if rc != 0:
+        raise RuntimeError(f"switchfl_b200 error {rc}: {lib.sfl_last_error().decode()}")
+    return out
+
+
+def device_q_update(rows: Sequence[Sequence[float]], device: int = 0, lib: Optional[C.CDLL] = None) -> np.ndarray:
+    """``sfl_kat_q_update``: the device's Q-update arithmetic on rows of (q, lr, reward, gamma, max_next, bootstrap)."""
+    lib = lib or load_library()
+    a = np.ascontiguousarray(rows, np.float64).reshape(-1, 6)
+    out = np.empty(len(a), np.float64)
+    rc = lib.sfl_kat_q_update(a.ctypes.data_as(C.POINTER(C.c_double)), len(a), out.ctypes.data_as(C.POINTER(C.c_double)), int(device))
     if rc != 0:
         raise RuntimeError(f"switchfl_b200 error {rc}: {lib.sfl_last_error().decode()}")
     return out
@@ -219,7 +235,8 @@ class Engine:
     def __init__(self, rail_map: RailMap, n_envs: int, device: str = "cuda:0", q_cap: int = 1024, pend_cap: int = 8,
                  max_steps: int = 100_000, dec_cap: int = 0, tick_cap: int = 0, ep_cap: int = 64, act_cap: int = 0,
                  ev_cap: int = 0, trace_sem: bool = False, lanes: Optional[int] = None, shared_q: bool = False,
-                 cta_warps: Optional[int] = None):
+                 cta_warps: Optional[int] = None, roomy: Optional[bool] = None, bind: bool = True):
+        """``bind=False`` creates the context only (no device buffers): enough for ``describe_launch``."""
         import torch
         self.torch = torch
         self.map = rail_map
@@ -233,6 +250,19 @@ class Engine:
         self._ck(self.lib.sfl_query_sizes(C.byref(rail_map.desc), C.byref(self.cfg), C.byref(self.sizes)))
         self.ctx = C.c_void_p()
         self._ck(self.lib.sfl_create(C.byref(rail_map.desc), C.byref(self.cfg), dev_index, C.byref(self.ctx)))
+        if lanes is not None:
+            self._ck(self.lib.sfl_set_lanes(self.ctx, int(lanes)))
+        if cta_warps is not None:
+            self._ck(self.lib.sfl_set_cta_warps(self.ctx, int(cta_warps)))
+        if roomy is not None:
+            self._ck(self.lib.sfl_set_roomy(self.ctx, int(bool(roomy))))
+        self.hparams = np.zeros(self.n_envs, HPARAMS_DT)
+        self._pinned = {}
+        self._pinned_ev = {}
+        self.buf = {}
+        self.reset_io_counters()
+        if not bind:
+            return
         z = lambda n: torch.zeros(max(int(n), 16), dtype=torch.uint8, device=self.device)
         s = self.sizes
         self.buf = {"state": z(s.state_bytes), "hparams": z(s.hparams_bytes), "counters": z(s.counters_bytes),
@@ -242,13 +272,6 @@ class Engine:
                     "shared_d": z(s.shared_d_bytes), "shared_c": z(s.shared_c_bytes)}
         b = Buffers(**{k: v.data_ptr() for k, v in self.buf.items()})
         self._ck(self.lib.sfl_bind(self.ctx, C.byref(b)))
-        if lanes is not None:
-            self._ck(self.lib.sfl_set_lanes(self.ctx, int(lanes)))
-        if cta_warps is not None:
-            self._ck(self.lib.sfl_set_cta_warps(self.ctx, int(cta_warps)))
-        self.hparams = np.zeros(self.n_envs, HPARAMS_DT)
-        self._pinned = {}
-        self._pinned_ev = {}
 
     # ------------------------------------------------------------------ helpers
     def _open(self, device):
@@ -269,6 +292,10 @@ class Engine:
         if rc != 0:
             raise RuntimeError(f"switchfl_b200 error {rc}: {self.lib.sfl_last_error().decode()}")
 
+    def reset_io_counters(self):
+        """Bytes copied host->device / device->host through this engine and kernel launches since the last call."""
+        self.h2d_bytes = self.d2h_bytes = self.n_launches = 0
+
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -276,6 +303,7 @@ class Engine:
         """host -> device through a reusable pinned staging buffer."""
         torch = self.torch
         raw = np.ascontiguousarray(host).view(np.uint8).reshape(-1)
+        self.h2d_bytes += raw.size
         dst = self.buf[name][:raw.size]
         st = self._pinned.get(name)
         if st is None or st.numel() < raw.size:
@@ -291,6 +319,7 @@ class Engine:
         """device -> host; small buffers that are read every step (counters, step records) go through a reusable pinned
         staging buffer, everything else through a plain copy."""
         t = self.buf[name] if nbytes is None else self.buf[name][:nbytes]
+        self.d2h_bytes += t.numel()
         if t.numel() > (8 << 20):
             return t.cpu().numpy()
         torch = self.torch
@@ -338,10 +367,20 @@ class Engine:
         """Lanes of a warp cooperating on one environment (a scheduling choice; results do not depend on it)."""
         return int(self.lib.sfl_get_lanes(self.ctx))
 
+    def describe_launch(self, mode: int = MODE_LEARN, traced: bool = False) -> str:
+        """The kernel instantiation + launch configuration ``run(mode)`` would use (``sfl_describe_launch``)."""
+        buf = C.create_string_buffer(256)
+        self._ck(self.lib.sfl_describe_launch(self.ctx, int(mode), int(traced), buf, 256))
+        return buf.value.decode()
+
+    def kernel_variant(self, mode: int = MODE_LEARN, traced: bool = False) -> str:
+        return self.describe_launch(mode, traced).split(" ")[0]
+
     def enable_q_init(self, on: bool = True):
         self._ck(self.lib.sfl_enable_q_init(self.ctx, int(on)))
 
     def run(self, mode: int, max_ticks: int):
+        self.n_launches += 1
         self._ck(self.lib.sfl_run(self.ctx, int(mode), int(max_ticks), self._stream()))
 
     def set_replay(self, actions: Optional[Sequence[Sequence[int]]], events: Optional[Sequence[np.ndarray]] = None):

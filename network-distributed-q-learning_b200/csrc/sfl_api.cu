@@ -49,6 +49,17 @@ static int d2h(void *h, const void *d, size_t n, void *) { memcpy(h, d, n); retu
 static int dev_zero(void *d, size_t n, void *) { memset(d, 0, n); return 0; }
 #endif
 
+// every entry point runs on its context's device and leaves the caller's current device as it found it
+struct DeviceGuard {
+#ifndef SFL_HOST_EMUL
+  int prev;
+  explicit DeviceGuard(int dev) : prev(-1) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+#else
+  explicit DeviceGuard(int) {}
+#endif
+};
+
 #ifndef SFL_MINB_BIG
 #define SFL_MINB_BIG 7                                 // CTAs per SM the large-map (tail in HBM) kernels are compiled for
 #endif
@@ -59,24 +70,32 @@ static int dev_zero(void *d, size_t n, void *) { memset(d, 0, n); return 0; }
 #define SFL_SMEM_BUDGET (56u * 1024u)                  // per CTA, so that four CTAs share an SM
 
 // ------------------------------------------------------------------------------------------------ kernels
-struct InitArgs { char *state; int n_envs, keep_q, keep_ninter, pad; };
+struct InitArgs { Layout L; char *state; int n_envs, keep_q, keep_ninter, pad; };
 
 struct InitEnv {          // the env block in HBM, no staging
+  const Layout *L;
   char *b;
   SFL_FN EnvHdr *h() const { return (EnvHdr *)b; }
-  SFL_FN int4 *tra() const { return (int4 *)(b + c_L.off_tra); }
-  SFL_FN int4 *trb() const { return (int4 *)(b + c_L.off_trb); }
-  SFL_FN SwS *sws() const { return (SwS *)(b + c_L.off_sws); }
-  SFL_FN double *q() const { return (double *)(b + c_L.off_q); }
+  SFL_FN int4 *tra() const { return (int4 *)(b + L->off_tra); }
+  SFL_FN int4 *trb() const { return (int4 *)(b + L->off_trb); }
+  SFL_FN SwS *sws() const { return (SwS *)(b + L->off_sws); }
+  SFL_FN double *q() const { return (double *)(b + L->off_q); }
 };
 
 SFL_FN void env_init(const InitArgs &ia, int env_id, int lane, int lanes) {
   InitEnv e;
-  e.b = ia.state + (size_t)env_id * c_L.env_stride;
-  for (int t = lane; t < c_L.T; t += lanes) { e.tra()[t] = make_int4(-1, 0, 0, 0); e.trb()[t] = make_int4(-1, 0xFFFF, 0, 0); }
-  if (!ia.keep_ninter) for (int s = lane; s < c_L.S; s += lanes) { SwS z; z.ninter = 0; z.pad = 0; z.eps_pow = 1.0; e.sws()[s] = z; }
+  e.L = &ia.L;
+  e.b = ia.state + (size_t)env_id * ia.L.env_stride;
+  // RailNetwork.reset (rail_network.py:135-149) never clears _train_prev_port / _train_source_port: a reset that continues
+  // a run (keep flags set: the next ep_cap segment of learn(), an exploit pause, test()) keeps them like the in-kernel reset
+  const int keep_ports = ia.keep_q || ia.keep_ninter;
+  for (int t = lane; t < ia.L.T; t += lanes) {
+    const int px = keep_ports ? e.trb()[t].x : -1;
+    e.tra()[t] = make_int4(-1, 0, 0, 0); e.trb()[t] = make_int4(px, 0xFFFF, 0, 0);
+  }
+  if (!ia.keep_ninter) for (int s = lane; s < ia.L.S; s += lanes) { SwS z; z.ninter = 0; z.pad = 0; z.eps_pow = 1.0; e.sws()[s] = z; }
   if (!ia.keep_q) {
-    size_t n = (size_t)c_L.q_cap * c_L.q_stride;
+    size_t n = (size_t)ia.L.q_cap * ia.L.q_stride;
     for (size_t i = lane; i < n; i += lanes) e.q()[i] = 0.0;
   }
   if (lane == 0) {
@@ -89,7 +108,7 @@ SFL_FN void env_init(const InitArgs &ia, int env_id, int lane, int lanes) {
 }
 
 #ifndef SFL_HOST_EMUL
-__global__ void __launch_bounds__(SFL_CTA_THREADS) k_init(InitArgs ia) {
+__global__ void __launch_bounds__(SFL_CTA_THREADS) k_init(const __grid_constant__ InitArgs ia) {
   int env_id = blockIdx.x * SFL_WARPS_PER_CTA + (threadIdx.x >> 5);
   if (env_id < ia.n_envs) env_init(ia, env_id, threadIdx.x & 31, 32);
 }
@@ -101,10 +120,10 @@ __global__ void __launch_bounds__(SFL_CTA_THREADS) k_init(InitArgs ia) {
 // ROOMY: compiled for 4 instead of 7 CTAs per SM (about 100 instead of 72 registers, no spills) -- for launches of the
 // large-map kernels that do not fill the SMs anyway (C3: 1024 one-environment warps per map, +10 %).
 template <int G, int KIND, bool TH, bool SQ, bool ONE, bool ROOMY = false>
-__global__ void __launch_bounds__(SFL_CTA_THREADS, TH ? (G == 32 ? 7 : 4) : (ROOMY ? 4 : SFL_MINB_BIG)) k_run() {
+__global__ void __launch_bounds__(SFL_CTA_THREADS, TH ? (G == 32 ? 7 : 4) : (ROOMY ? 4 : SFL_MINB_BIG)) k_run(const __grid_constant__ KArgs K) {
   const int slot = threadIdx.x / G;                    // environment slot inside the CTA
   const int env_id = blockIdx.x * (blockDim.x / G) + slot;
-  env_run<G, KIND, TH, SQ, ONE>(env_id, (unsigned)slot * c_ra.env_smem, nullptr);
+  env_run<G, KIND, TH, SQ, ONE>(K, env_id, (unsigned)slot * K.ra.env_smem, nullptr);
 }
 
 __global__ void k_sum(const sfl_env_counters *c, int n, unsigned long long *out) {
@@ -158,7 +177,13 @@ __global__ void __launch_bounds__(512) k_distance_map(const uint16_t *grid, int 
   if (SMEM) for (int i = threadIdx.x; i < n; i += blockDim.x) gd[i] = d[i];
 }
 
-typedef void (*run_kernel_t)();
+// known-answer hook: the device's TD arithmetic on caller operands (rows of {q, lr, reward, gamma, max_next, bootstrap})
+__global__ void k_kat_q_update(const double *in, int n, double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = td_value(in[6 * i], in[6 * i + 1], in[6 * i + 2], in[6 * i + 3], in[6 * i + 4], in[6 * i + 5] != 0.0);
+}
+
+typedef void (*run_kernel_t)(const KArgs);
 // `one`: every train has its own lane (T <= G): the production kernels have a single-pass variant for that; the full and
 // the shared-table kernels always run the general chunked loops.
 template <int G> static run_kernel_t pick_kernel_g(int kind, int th, int sq, int one, int roomy) {
@@ -192,13 +217,38 @@ struct Ctx {
   Layout L;
   sfl_config cfg;
   sfl_buffers bufs;
-  int bound, device, q_init_on, lanes, sm_count, cta_warps;
+  int bound, device, q_init_on, lanes, sm_count, cta_warps, roomy;        // roomy: -1 automatic, 0 / 1 forced
   unsigned hot_bytes, env_smem, tail_hot;
   void *blob;          // device block holding every map table
   void *sum_buf;       // 2 x u64
 };
 
-static int set_constants(const Ctx *c, const RunArgs *ra, void *stream);
+// ------------------------------------------------------------------------------------------------ launch plan
+// Which k_run instantiation a launch of `kind` uses and its launch configuration -- shared by sfl_run and
+// sfl_describe_launch, so that tests can pin exactly the instantiations the benchmark times.
+struct LaunchPlan { int G, th, one, roomy, threads, grid; size_t smem; };
+static int plan_launch(const Ctx *c, int kind, LaunchPlan *lp) {
+  const int G = c->lanes;
+  // Warps per CTA: the kernels are compiled for at most SFL_WARPS_PER_CTA; small launches use smaller CTAs so that the
+  // CTAs spread evenly over the SMs (1024 one-env warps as 256 CTAs leave SMs with 8 or 4 warps; as 1024 CTAs with 7).
+  int cta_warps = c->cta_warps;
+  const long warps = ((long)c->cfg.n_envs * G + 31) / 32;
+  if (cta_warps <= 0) {
+    cta_warps = SFL_WARPS_PER_CTA;
+    while (cta_warps > 1 && warps / cta_warps < 8L * c->sm_count) cta_warps /= 2;      // fewer than 8 CTAs per SM: halve
+  }
+  int threads = 32 * cta_warps;                        // then shrink the CTA until its environments fit shared memory
+  while (threads > 32 && (size_t)c->env_smem * (threads / G) > SFL_SMEM_BUDGET) threads /= 2;
+  const int envs_per_cta = threads / G;
+  lp->smem = (size_t)c->env_smem * envs_per_cta;
+  if (lp->smem > 227u * 1024u) return fail(SFL_E_ARG, "environment state does not fit shared memory with this many lanes per env: use more lanes%s");
+  lp->G = G; lp->threads = threads; lp->grid = (c->cfg.n_envs + envs_per_cta - 1) / envs_per_cta;
+  lp->th = (int)c->tail_hot; lp->one = c->L.T <= G && !c->cfg.shared_q && kind != K_FULL;
+  int roomy = c->roomy >= 0 ? c->roomy : (warps <= 16L * c->sm_count);                   // one wave even at 4 CTAs per SM
+  lp->roomy = roomy && !lp->th && !c->cfg.shared_q && kind == K_LEARN && G >= 16;        // the only roomy instantiations
+  return 0;
+}
+
 
 // Shared-memory staging plan for c->lanes lanes per environment: the whole non-Q state (header, train records, pending
 // lists, semaphores, rewards, per-switch counters) when that still leaves room for 16 warps per SM,
@@ -241,18 +291,6 @@ static int make_layout(const sfl_map_desc *map, const sfl_config *cfg, Layout *L
   return SFL_OK;
 }
 
-static int set_constants(const Ctx *c, const RunArgs *ra, void *stream) {
-#ifndef SFL_HOST_EMUL
-  if (cudaMemcpyToSymbolAsync(c_m, &c->m, sizeof(DevMap), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess) return 1;
-  if (cudaMemcpyToSymbolAsync(c_L, &c->L, sizeof(Layout), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess) return 1;
-  if (ra && cudaMemcpyToSymbolAsync(c_ra, ra, sizeof(RunArgs), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess) return 1;
-#else
-  c_m = c->m; c_L = c->L;
-  if (ra) c_ra = *ra;
-#endif
-  return 0;
-}
-
 extern "C" {
 
 int sfl_abi_version(void) { return SFL_ABI_VERSION; }
@@ -265,7 +303,7 @@ int sfl_distance_map(const uint16_t *grid, int32_t H, int32_t W, const int32_t *
 #ifndef SFL_HOST_EMUL
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SFL_E_CUDA, "no CUDA device: this library has no CPU path%s");
-  CU(cudaSetDevice(device));
+  DeviceGuard guard(device);
   uint16_t *dg = nullptr; int *dt = nullptr, *dd = nullptr;
   if (cudaMalloc(&dg, (size_t)H * W * 2) != cudaSuccess || cudaMalloc(&dt, (size_t)n_targets * 4) != cudaSuccess ||
       cudaMalloc(&dd, n * 4 * n_targets) != cudaSuccess) { cudaFree(dg); cudaFree(dt); cudaFree(dd); return fail(SFL_E_CUDA, "device alloc failed%s"); }
@@ -311,6 +349,32 @@ int sfl_distance_map(const uint16_t *grid, int32_t H, int32_t W, const int32_t *
 #endif
 }
 const char *sfl_last_error(void) { return g_err; }
+
+int sfl_kat_q_update(const double *operands, int32_t n, double *out, int device) {
+  if (!operands || !out || n < 0) return fail(SFL_E_ARG, "bad argument%s");
+  if (!n) return SFL_OK;
+#ifndef SFL_HOST_EMUL
+  int ndev = 0, prev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SFL_E_CUDA, "no CUDA device: this library has no CPU path%s");
+  cudaGetDevice(&prev);
+  CU(cudaSetDevice(device));
+  double *din = nullptr, *dout = nullptr;
+  int rc = SFL_OK;
+  if (cudaMalloc(&din, (size_t)n * 48) != cudaSuccess || cudaMalloc(&dout, (size_t)n * 8) != cudaSuccess) rc = fail(SFL_E_CUDA, "device alloc failed%s");
+  else if (cudaMemcpy(din, operands, (size_t)n * 48, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(SFL_E_CUDA, "upload failed%s");
+  else {
+    k_kat_q_update<<<(n + 127) / 128, 128>>>(din, n, dout);
+    if (cudaGetLastError() != cudaSuccess || cudaMemcpy(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(SFL_E_CUDA, "kat kernel failed%s");
+  }
+  cudaFree(din); cudaFree(dout);
+  cudaSetDevice(prev);
+  return rc;
+#else
+  (void)device;
+  for (int i = 0; i < n; i++) out[i] = td_value(operands[6 * i], operands[6 * i + 1], operands[6 * i + 2], operands[6 * i + 3], operands[6 * i + 4], operands[6 * i + 5] != 0.0);
+  return SFL_OK;
+#endif
+}
 
 int sfl_query_sizes(const sfl_map_desc *map, const sfl_config *cfg, sfl_sizes *out) {
   Layout L; int a_max;
@@ -375,12 +439,13 @@ int sfl_create(const sfl_map_desc *map, const sfl_config *cfg, int device, void 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(SFL_E_CUDA, "no CUDA device: this library has no CPU path%s");
-  CU(cudaSetDevice(device));
+  if (device < 0 || device >= ndev) return fail(SFL_E_ARG, "no such CUDA device%s");
   CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
 #endif
+  DeviceGuard dg(device);
   Ctx *c = new (std::nothrow) Ctx();
   if (!c) return fail(SFL_E_NOMEM, "host alloc%s");
-  c->L = L; c->cfg = *cfg; c->bound = 0; c->device = device; c->q_init_on = 0; c->cta_warps = 0; c->blob = nullptr; c->sum_buf = nullptr; c->sm_count = sm_count;
+  c->L = L; c->cfg = *cfg; c->bound = 0; c->device = device; c->q_init_on = 0; c->cta_warps = 0; c->roomy = -1; c->blob = nullptr; c->sum_buf = nullptr; c->sm_count = sm_count;
   memset(&c->bufs, 0, sizeof(c->bufs));
   auto pcell = [&](int cell) { return cell < 0 ? -1 : (cell / W + 1) * Wp + (cell % W + 1); };
   // ---- pack every table into one host image, 16-byte aligned sections
@@ -424,10 +489,10 @@ int sfl_create(const sfl_map_desc *map, const sfl_config *cfg, int device, void 
     dist[((size_t)k * Hp * Wp + (r + 1) * Wp + cc + 1) * 4 + d] = map->dist[(((size_t)k * H + r) * W + cc) * 4 + d];
   int8_t *qi = (int8_t *)&img[o_qi];
   for (int i = 0; i < NP * NT; i++) qi[i] = map->qinit_act[i] < 0 ? (int8_t)-1 : (int8_t)(map->qinit_act[i] | (map->qinit_final[i] ? 16 : 0));
-  if (dev_alloc(&c->blob, img.size()) || dev_alloc(&c->sum_buf, 16)) { delete c; return fail(SFL_E_CUDA, "device alloc of map constants failed%s"); }
-  if (h2d(c->blob, img.data(), img.size(), nullptr)) { delete c; return fail(SFL_E_CUDA, "upload of map constants failed%s"); }
+  if (dev_alloc(&c->blob, img.size()) || dev_alloc(&c->sum_buf, 16)) { sfl_destroy(c); return fail(SFL_E_CUDA, "device alloc of map constants failed%s"); }
+  if (h2d(c->blob, img.data(), img.size(), nullptr)) { sfl_destroy(c); return fail(SFL_E_CUDA, "upload of map constants failed%s"); }
 #ifndef SFL_HOST_EMUL
-  CU(cudaDeviceSynchronize());
+  if (cudaDeviceSynchronize() != cudaSuccess) { sfl_destroy(c); return fail(SFL_E_CUDA, "upload of map constants failed%s"); }
 #endif
   char *b = (char *)c->blob;
   DevMap &m = c->m;
@@ -460,6 +525,7 @@ int sfl_create(const sfl_map_desc *map, const sfl_config *cfg, int device, void 
 int sfl_destroy(void *ctx) {
   Ctx *c = (Ctx *)ctx;
   if (!c) return SFL_OK;
+  DeviceGuard dg(c->device);
   if (c->blob) dev_free(c->blob);
   if (c->sum_buf) dev_free(c->sum_buf);
   delete c;
@@ -496,6 +562,27 @@ int sfl_set_cta_warps(void *ctx, int warps) {
   return SFL_OK;
 }
 
+int sfl_set_roomy(void *ctx, int roomy) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c) return fail(SFL_E_ARG, "null ctx%s");
+  if (roomy < -1 || roomy > 1) return fail(SFL_E_ARG, "roomy must be -1 (automatic), 0 or 1%s");
+  c->roomy = roomy;
+  return SFL_OK;
+}
+
+int sfl_describe_launch(void *ctx, int mode, int traced, char *buf, int cap) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || !buf || cap < 1) return fail(SFL_E_ARG, "null argument%s");
+  const int trace = traced || mode == SFL_MODE_STEP || mode == SFL_MODE_REPLAY;
+  const int kind = trace ? K_FULL : (mode == SFL_MODE_GREEDY ? K_GREEDY : K_LEARN);
+  LaunchPlan lp;
+  if (plan_launch(c, kind, &lp)) return SFL_E_ARG;
+  static const char *kinds[] = {"learn", "greedy", "full"};
+  snprintf(buf, (size_t)cap, "k_run<G=%d,KIND=%s,TH=%d,SQ=%d,ONE=%d,ROOMY=%d> grid=%d block=%d smem=%zu", lp.G, kinds[kind], lp.th,
+           c->cfg.shared_q ? 1 : 0, lp.one, lp.roomy, lp.grid, lp.threads, lp.smem);
+  return SFL_OK;
+}
+
 int sfl_get_lanes(void *ctx) {
   Ctx *c = (Ctx *)ctx;
   return c ? c->lanes : SFL_E_ARG;
@@ -505,15 +592,14 @@ int sfl_reset(void *ctx, int keep, void *stream) {
   Ctx *c = (Ctx *)ctx;
   if (!c) return fail(SFL_E_ARG, "null ctx%s");
   if (!c->bound) return fail(SFL_E_STATE, "sfl_bind first%s");
-  InitArgs ia; ia.state = (char *)c->bufs.state; ia.n_envs = c->cfg.n_envs; ia.keep_q = keep & 1; ia.keep_ninter = (keep >> 1) & 1; ia.pad = 0;
+  DeviceGuard dg(c->device);
+  InitArgs ia; ia.L = c->L; ia.state = (char *)c->bufs.state; ia.n_envs = c->cfg.n_envs; ia.keep_q = keep & 1; ia.keep_ninter = (keep >> 1) & 1; ia.pad = 0;
   CK(dev_zero(c->bufs.counters, (size_t)c->cfg.n_envs * sizeof(sfl_env_counters), stream));
 #ifndef SFL_HOST_EMUL
   int grid = (c->cfg.n_envs + SFL_WARPS_PER_CTA - 1) / SFL_WARPS_PER_CTA;
-  CK(set_constants(c, nullptr, stream));
   k_init<<<grid, SFL_CTA_THREADS, 0, (cudaStream_t)stream>>>(ia);
   CU(cudaGetLastError());
 #else
-  set_constants(c, nullptr, stream);
   for (int i = 0; i < c->cfg.n_envs; i++) env_init(ia, i, 0, 1);
 #endif
   return SFL_OK;
@@ -534,8 +620,11 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   if ((mode == SFL_MODE_REPLAY || mode == SFL_MODE_STEP) && (!c->bufs.replay_act || c->cfg.act_cap < 1))
     return fail(SFL_E_ARG, "replay / step mode needs replay_act (act_cap >= 1)%s");
   if (mode == SFL_MODE_STEP && !c->bufs.step_out) return fail(SFL_E_ARG, "step mode needs step_out%s");
-  RunArgs ra;
-  memset(&ra, 0, sizeof(ra));
+  DeviceGuard dg(c->device);
+  KArgs K;
+  memset(&K, 0, sizeof(K));
+  K.m = c->m; K.L = c->L;
+  RunArgs &ra = K.ra;
   ra.mode = mode; ra.max_ticks = max_ticks; ra.n_envs = c->cfg.n_envs; ra.trace_sem = c->cfg.trace_sem;
   ra.dec_cap = c->cfg.dec_cap; ra.tick_cap = c->cfg.tick_cap; ra.ep_cap = c->cfg.ep_cap; ra.act_cap = c->cfg.act_cap;
   ra.ev_cap = c->cfg.ev_cap; ra.max_steps = c->cfg.max_steps; ra.q_init_on = c->q_init_on;
@@ -555,38 +644,24 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   const int trace = ra.trace_dec || ra.trace_tick || mode == SFL_MODE_STEP || mode == SFL_MODE_REPLAY;
   const int kind = trace ? K_FULL : (mode == SFL_MODE_GREEDY ? K_GREEDY : K_LEARN);
 #ifndef SFL_HOST_EMUL
-  const int G = c->lanes;
-  // Warps per CTA: the kernels are compiled for at most SFL_WARPS_PER_CTA; small launches use smaller CTAs so that the
-  // CTAs spread evenly over the SMs (1024 one-env warps as 256 CTAs leave SMs with 8 or 4 warps; as 1024 CTAs with 7).
-  int cta_warps = c->cta_warps;
-  if (cta_warps <= 0) {
-    const long warps = ((long)c->cfg.n_envs * G + 31) / 32;
-    cta_warps = SFL_WARPS_PER_CTA;
-    while (cta_warps > 1 && warps / cta_warps < 8L * c->sm_count) cta_warps /= 2;      // fewer than 8 CTAs per SM: halve
-  }
-  int threads = 32 * cta_warps;                        // then shrink the CTA until its environments fit shared memory
-  while (threads > 32 && (size_t)c->env_smem * (threads / G) > SFL_SMEM_BUDGET) threads /= 2;
-  const int envs_per_cta = threads / G;
-  const size_t smem = (size_t)c->env_smem * envs_per_cta;
-  if (smem > 227u * 1024u) return fail(SFL_E_ARG, "environment state does not fit shared memory with this many lanes per env: use more lanes%s");
-  int grid = (c->cfg.n_envs + envs_per_cta - 1) / envs_per_cta;
+  LaunchPlan lp;
+  if (plan_launch(c, kind, &lp)) return SFL_E_ARG;
   if (c->cfg.shared_q && trace) return fail(SFL_E_ARG, "shared-table mode has no trace / step variants%s");
-  const int roomy = ((long)c->cfg.n_envs * G + 31) / 32 <= 16L * c->sm_count;            // one wave even at 4 CTAs per SM
-  run_kernel_t k = pick_kernel(G, kind, (int)c->tail_hot, c->cfg.shared_q, c->L.T <= G, roomy);
+  const int grid = lp.grid, threads = lp.threads;
+  const size_t smem = lp.smem;
+  run_kernel_t k = pick_kernel(lp.G, kind, lp.th, c->cfg.shared_q, lp.one, lp.roomy);
   CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(set_constants(c, &ra, stream));
-  k<<<grid, threads, smem, (cudaStream_t)stream>>>();
+  k<<<grid, threads, smem, (cudaStream_t)stream>>>(K);
   CU(cudaGetLastError());
 #else
   static char host_scratch[32 * SFL_MAX_T + 2 * SFL_MAX_T + 64];
-  set_constants(c, &ra, stream);
   for (int i = 0; i < c->cfg.n_envs; i++) {
     if (c->cfg.shared_q) {
       if (trace) return fail(SFL_E_ARG, "shared-table mode has no trace / step variants%s");
-      if (kind == K_GREEDY) env_run<1, K_GREEDY, true, true, false>(i, 0u, host_scratch); else env_run<1, K_LEARN, true, true, false>(i, 0u, host_scratch);
-    } else if (kind == K_FULL) env_run<1, K_FULL, true, false, false>(i, 0u, host_scratch);
-    else if (kind == K_GREEDY) env_run<1, K_GREEDY, true, false, false>(i, 0u, host_scratch);
-    else env_run<1, K_LEARN, true, false, false>(i, 0u, host_scratch);
+      if (kind == K_GREEDY) env_run<1, K_GREEDY, true, true, false>(K, i, 0u, host_scratch); else env_run<1, K_LEARN, true, true, false>(K, i, 0u, host_scratch);
+    } else if (kind == K_FULL) env_run<1, K_FULL, true, false, false>(K, i, 0u, host_scratch);
+    else if (kind == K_GREEDY) env_run<1, K_GREEDY, true, false, false>(K, i, 0u, host_scratch);
+    else env_run<1, K_LEARN, true, false, false>(K, i, 0u, host_scratch);
   }
 #endif
   return SFL_OK;
@@ -595,11 +670,12 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
 int sfl_shared_q_apply(void *ctx, void *stream) {
   Ctx *c = (Ctx *)ctx;
   if (!c || !c->bound) return fail(SFL_E_STATE, "sfl_bind first%s");
+  DeviceGuard dg(c->device);
   if (!c->cfg.shared_q) return fail(SFL_E_STATE, "context was not created in shared-table mode%s");
   const size_t n = (size_t)c->m.NP * c->m.NT * 48u * (size_t)c->L.a_max;
   double *q = (double *)c->bufs.shared_q; long long *d = (long long *)c->bufs.shared_d; int *cn = (int *)c->bufs.shared_c;
 #ifndef SFL_HOST_EMUL
-  k_shared_apply<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(q, d, cn, n);
+  k_shared_apply<<<c->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(q, d, cn, n);
   CU(cudaGetLastError());
 #else
   (void)stream;
@@ -611,10 +687,11 @@ int sfl_shared_q_apply(void *ctx, void *stream) {
 int sfl_total_decisions(void *ctx, uint64_t *decisions, uint64_t *ticks, void *stream) {
   Ctx *c = (Ctx *)ctx;
   if (!c || !c->bound) return fail(SFL_E_STATE, "sfl_bind first%s");
+  DeviceGuard dg(c->device);
   unsigned long long out[2] = {0, 0};
 #ifndef SFL_HOST_EMUL
   CK(dev_zero(c->sum_buf, 16, stream));
-  k_sum<<<148, 256, 0, (cudaStream_t)stream>>>((const sfl_env_counters *)c->bufs.counters, c->cfg.n_envs, (unsigned long long *)c->sum_buf);
+  k_sum<<<c->sm_count, 256, 0, (cudaStream_t)stream>>>((const sfl_env_counters *)c->bufs.counters, c->cfg.n_envs, (unsigned long long *)c->sum_buf);
   CU(cudaGetLastError());
   CK(d2h(out, c->sum_buf, 16, stream));
 #else
@@ -629,6 +706,7 @@ int sfl_total_decisions(void *ctx, uint64_t *decisions, uint64_t *ticks, void *s
 int sfl_export_q(void *ctx, int env, uint32_t *keys_host, double *vals_host, int cap_rows, int *n_rows, void *stream) {
   Ctx *c = (Ctx *)ctx;
   if (!c || !c->bound) return fail(SFL_E_STATE, "sfl_bind first%s");
+  DeviceGuard dg(c->device);
   if (env < 0 || env >= c->cfg.n_envs || !n_rows) return fail(SFL_E_ARG, "bad env / n_rows%s");
   const Layout &L = c->L;
   size_t n = (size_t)L.q_cap * L.q_stride;
@@ -652,11 +730,13 @@ int sfl_export_q(void *ctx, int env, uint32_t *keys_host, double *vals_host, int
 int sfl_import_q(void *ctx, int env, const uint32_t *keys_host, const double *vals_host, int n_rows, void *stream) {
   Ctx *c = (Ctx *)ctx;
   if (!c || !c->bound) return fail(SFL_E_STATE, "sfl_bind first%s");
+  DeviceGuard dg(c->device);
   if (env < 0 || env >= c->cfg.n_envs || n_rows < 0 || n_rows >= c->cfg.q_cap) return fail(SFL_E_ARG, "bad env / n_rows%s");
   const Layout &L = c->L;
   size_t n = (size_t)L.q_cap * L.q_stride;
   std::vector<double> img(n, 0.0);
   unsigned mask = (unsigned)L.q_cap - 1u;
+  int distinct = 0;
   for (int r = 0; r < n_rows; r++) {
     unsigned key = keys_host[r];
     unsigned i = (key * 2654435761u) >> 7;
@@ -664,6 +744,7 @@ int sfl_import_q(void *ctx, int env, const uint32_t *keys_host, const double *va
       i &= mask;
       unsigned long long k;
       memcpy(&k, &img[(size_t)i * L.q_stride], 8);
+      if (k == 0) distinct++;
       if (k == 0 || k == (unsigned long long)key + 1ull) break;
       i++;
     }
@@ -673,7 +754,7 @@ int sfl_import_q(void *ctx, int env, const uint32_t *keys_host, const double *va
   }
   char *base = (char *)c->bufs.state + (size_t)env * L.env_stride;
   CK(h2d(base + L.off_q, img.data(), n * 8, stream));
-  int q_rows = n_rows;
+  int q_rows = distinct;                         // repeated keys overwrite their row
   CK(h2d(base + offsetof(EnvHdr, q_rows), &q_rows, 4, stream));
 #ifndef SFL_HOST_EMUL
   CU(cudaStreamSynchronize((cudaStream_t)stream));

@@ -141,6 +141,8 @@ struct EnvHdr {            // 128 bytes at the start of every env block
   int last_next_sw;                    // "next_switch" of the most recent decision (SFL_MODE_STEP)
   int eps_tag;                         // epsilon-greedy draw cache: pair of decisions (step_counter >> 1) the words below belong to
   unsigned eps_z, eps_w;               //   words 2 and 3 of that pair's Philox block (the odd decision of the pair uses them)
+  unsigned long long forced_stops, stop_actions, arrived_trains;     // lifetime statistics (sfl_env_counters)
+  unsigned long long pad_;
 };
 
 // Per-train records (16 bytes each, one vector load per phase):
@@ -167,12 +169,14 @@ struct RunArgs {           // per-launch arguments
   const int8_t *replay_act; const int *replay_ev;     // ev: [env][ev_cap][3] = (tick, train, duration), tick-sorted, tick<0 ends
 };
 
-// map constants, env-block layout and launch arguments live in constant memory (set by sfl_run / sfl_reset before the
-// launch, in stream order), so device functions read them as constant-bank operands.  All contexts of one process must
-// therefore launch on one stream.
-SFL_CONST DevMap c_m;
-SFL_CONST Layout c_L;
-SFL_CONST RunArgs c_ra;
+// Map constants, env-block layout and launch arguments travel as ONE __grid_constant__ kernel parameter (constant bank,
+// the same operand cost as __constant__ symbols) -- so contexts are independent of each other: any stream, any device,
+// several maps in flight at once.  Device functions receive it as `K`; c_m / c_L / c_ra name its three parts.
+struct KArgs { DevMap m; Layout L; RunArgs ra; };
+#define SFL_K const KArgs &K
+#define c_m (K.m)
+#define c_L (K.L)
+#define c_ra (K.ra)
 
 #if SFL_DEV
 extern __shared__ __align__(16) char g_smem[];     // the CTA's dynamic shared memory
@@ -189,17 +193,18 @@ SFL_FN char *hot_ptr(hot_t o) { return o; }
 template <bool TH, bool SQ_ = false> struct EnvT {
   static const bool SQ = SQ_;
   static const bool HOT_TAIL = TH;
+  const KArgs *kp;         // the launch's parameter block (methods below read the layout through it)
   hot_t hot;               // staged copy of the first hot_bytes of the env block (the env block itself on the host build)
   char *gb;                // the env block in HBM
   SFL_FN EnvHdr *h() const { return (EnvHdr *)hot_ptr(hot); }
-  SFL_FN int4 *tra() const { return (int4 *)(hot_ptr(hot) + c_L.off_tra); }
-  SFL_FN int4 *trb() const { return (int4 *)(hot_ptr(hot) + c_L.off_trb); }
+  SFL_FN int4 *tra() const { return (int4 *)(hot_ptr(hot) + kp->L.off_tra); }
+  SFL_FN int4 *trb() const { return (int4 *)(hot_ptr(hot) + kp->L.off_trb); }
   SFL_FN char *tail() const { return TH ? hot_ptr(hot) : gb; }
-  SFL_FN int2 *pend() const { return (int2 *)(tail() + c_L.off_pend); }
-  SFL_FN int4 *sem() const { return (int4 *)(tail() + c_L.off_sem); }
-  SFL_FN int *rewards() const { return (int *)(tail() + c_L.off_rewards); }
-  SFL_FN SwS *sws() const { return (SwS *)(tail() + c_L.off_sws); }
-  SFL_FN double *q() const { return (double *)(gb + c_L.off_q); }
+  SFL_FN int2 *pend() const { return (int2 *)(tail() + kp->L.off_pend); }
+  SFL_FN int4 *sem() const { return (int4 *)(tail() + kp->L.off_sem); }
+  SFL_FN int *rewards() const { return (int *)(tail() + kp->L.off_rewards); }
+  SFL_FN SwS *sws() const { return (SwS *)(tail() + kp->L.off_sws); }
+  SFL_FN double *q() const { return (double *)(gb + kp->L.off_q); }
   // Who holds the record of port p (-1: nobody).  When the semaphore table stays in HBM (large maps) a byte mirror of
   // the holders lives in shared memory: "is there a record / is it mine / is its holder stopped" -- most of what the
   // decision and the per-tick semaphore phases ask -- is then answered without touching global memory.
@@ -219,12 +224,13 @@ template <bool TH, bool SQ_ = false> struct EnvT {
 //        replay injects recorded events instead of drawing, so `inj` (durations injected this tick) aliases it
 //   occ  train standing on my destination cell, or -1;   blk  movement blocked
 struct Scratch {
+  const KArgs *kp;
   hot_t base;
   SFL_FN int4 *tmp() const { return (int4 *)hot_ptr(base); }
-  SFL_FN int4 *rng() const { return (int4 *)(hot_ptr(base) + 16 * c_L.T); }
-  SFL_FN int *inj() const { return (int *)(hot_ptr(base) + 16 * c_L.T); }
-  SFL_FN int8_t *occ() const { return (int8_t *)(hot_ptr(base) + 32 * c_L.T); }
-  SFL_FN uint8_t *blk() const { return (uint8_t *)(hot_ptr(base) + 33 * c_L.T); }
+  SFL_FN int4 *rng() const { return (int4 *)(hot_ptr(base) + 16 * kp->L.T); }
+  SFL_FN int *inj() const { return (int *)(hot_ptr(base) + 16 * kp->L.T); }
+  SFL_FN int8_t *occ() const { return (int8_t *)(hot_ptr(base) + 32 * kp->L.T); }
+  SFL_FN uint8_t *blk() const { return (uint8_t *)(hot_ptr(base) + 33 * kp->L.T); }
 };
 #if SFL_DEV
 __host__
@@ -242,7 +248,7 @@ struct Hp {
 // value the replay / step / trace paths stayed in the hot kernels and cost the large-map kernels 8 % (registers and
 // instruction fetch at 72 registers).  The third kind carries everything: any mode, traces, the step protocol.
 enum { K_LEARN = 0, K_GREEDY = 1, K_FULL = 2 };
-template <int KIND> SFL_FN int run_mode() { return KIND == K_LEARN ? (int)SFL_MODE_LEARN : KIND == K_GREEDY ? (int)SFL_MODE_GREEDY : c_ra.mode; }
+template <int KIND> SFL_FN int run_mode(SFL_K) { return KIND == K_LEARN ? (int)SFL_MODE_LEARN : KIND == K_GREEDY ? (int)SFL_MODE_GREEDY : c_ra.mode; }
 
 // ------------------------------------------------------------------------------------------------ Philox4x32-10
 struct U4 { unsigned x, y, z, w; };
@@ -266,9 +272,9 @@ SFL_FN U4 philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigne
 // for RailEnvAction a.  sfl_create rejects maps with a transition into a non-rail cell, so "new cell is rail"
 // (the reference's new_cell_valid) is implied by a valid transition.
 struct Mv { int cell, dir, valid; };
-SFL_FN unsigned mv_entry(int cell, int dir) { return c_m.move[(size_t)cell * 4 + dir]; }
+SFL_FN unsigned mv_entry(SFL_K, int cell, int dir) { return c_m.move[(size_t)cell * 4 + dir]; }
 SFL_FN int mv_valid(unsigned e, int action) { return (e >> (3 * action)) & 1; }
-SFL_FN Mv mv_apply(unsigned e, int action, int cell) {
+SFL_FN Mv mv_apply(SFL_K, unsigned e, int action, int cell) {
   unsigned f = (e >> (3 * action)) & 7u;
   int nd = (int)(f >> 1);
   int delta = (nd & 1) ? (2 - nd) : (nd - 1) * c_m.Wp;
@@ -277,7 +283,7 @@ SFL_FN Mv mv_apply(unsigned e, int action, int cell) {
   r.dir = nd; r.valid = (int)(f & 1u);
   return r;
 }
-SFL_FN Mv check_action(int action, int cell, int dir) { return mv_apply(mv_entry(cell, dir), action, cell); }
+SFL_FN Mv check_action(SFL_K, int action, int cell, int dir) { return mv_apply(K, mv_entry(K, cell, dir), action, cell); }
 
 SFL_FN int is_moving(int a) { return a >= A_LEFT && a <= A_RIGHT; }
 
@@ -316,7 +322,7 @@ SFL_FN int port_blocked(Env e, int next_port, int out_port, int me, int now) {
 // exactly where the reference's __check_entry (distr_q.py:47-57) would insert a dict entry, so the exported
 // key set equals the reference's.
 template <class Env>
-SFL_NI double *q_row(Env e, const Hp hp, unsigned key) {
+SFL_NI double *q_row(SFL_K, Env e, const Hp hp, unsigned key) {
   if (Env::SQ) return c_ra.sq_q + (size_t)key * c_L.a_max;              // shared-table mode: dense, initialised by the host
   unsigned mask = (unsigned)c_L.q_cap - 1u;
   unsigned i = (key * 2654435761u) >> 7;
@@ -366,41 +372,35 @@ SFL_FN double lr_pow(double rate, int n) {
   return r;
 }
 
-// distr_q.py:419-447 update (fp64, Python operator order, no FMA contraction)
+// distr_q.py:441-447 (fp64, Python operator order, no FMA contraction):
+//   bootstrap (successor switch differs): (1 - lr) * Q + lr * (reward + gamma * max_a' Q')    else: (1 - lr) * Q + lr * reward
+SFL_FN double td_value(double q, double lr, double reward, double gamma, double mq, int bootstrap) {
+  const double one_m = dadd(1.0, -lr);
+  return bootstrap ? dadd(dmul(one_m, q), dmul(lr, dadd(reward, dmul(gamma, mq)))) : dadd(dmul(one_m, q), dmul(lr, reward));
+}
+
+// distr_q.py:419-447 update
 template <class Env>
-SFL_NI void q_update(Env e, const Hp hp, unsigned key, int action, double reward,
+SFL_NI void q_update(SFL_K, Env e, const Hp hp, unsigned key, int action, double reward,
                      const double *next_row, int prev_sw, int next_sw) {
-  double *row = q_row(e, hp, key);
+  double *row = q_row(K, e, hp, key);
   double lr = hp->lr;
   if (hp->lr_decay_rate != 1.0) lr = dmul(lr, lr_pow(hp->lr_decay_rate, e.sws()[prev_sw].ninter));
-  double one_m = dadd(1.0, -lr);
-  double q = row[action];
+  const double q = row[action];
+  double mq = 0.0;
+  if (next_sw != prev_sw && next_row) {                          // distr_q.py:449-466 max_q ignores the mask; max_q(None) = 0
+    int A = c_m.sw[next_sw].y;
+    mq = next_row[0];
+    SFL_NU
+    for (int a = 1; a < A; a++) { const double v = next_row[a]; mq = v > mq ? v : mq; }
+  }
+  const double nq = td_value(q, lr, reward, hp->gamma, mq, next_sw != prev_sw);
   if (Env::SQ) {                                                         // shared table: propose the TD step, leave the table alone
-    double mq = 0.0;
-    if (next_sw != prev_sw && next_row) {
-      int A = c_m.sw[next_sw].y;
-      mq = next_row[0];
-      SFL_NU
-      for (int a = 1; a < A; a++) { const double v = next_row[a]; mq = v > mq ? v : mq; }
-    }
-    const double nq = next_sw != prev_sw ? dadd(dmul(one_m, q), dmul(lr, dadd(reward, dmul(hp->gamma, mq))))
-                                         : dadd(dmul(one_m, q), dmul(lr, reward));
     const size_t i = (size_t)key * c_L.a_max + action;
     shared_add(c_ra.sq_d + i, c_ra.sq_c + i, (long long)llrint((nq - q) * 16777216.0));
     return;
   }
-  if (next_sw != prev_sw) {
-    double mq = 0.0;
-    if (next_row) {                                             // distr_q.py:449-466 max_q ignores the mask
-      int A = c_m.sw[next_sw].y;
-      mq = next_row[0];
-      SFL_NU
-      for (int a = 1; a < A; a++) { const double v = next_row[a]; mq = v > mq ? v : mq; }
-    }
-    row[action] = dadd(dmul(one_m, q), dmul(lr, dadd(reward, dmul(hp->gamma, mq))));
-  } else {
-    row[action] = dadd(dmul(one_m, q), dmul(lr, reward));
-  }
+  row[action] = nq;
 }
 
 // distr_q.py:468-490 max_action
@@ -419,7 +419,7 @@ SFL_FN int max_action(const double *row, int A, int mask) {
 
 // ------------------------------------------------------------------------------------------------ E3
 template <class Env>
-SFL_FN void sem_delete_owned(Env e, int port, int h) {
+SFL_FN void sem_delete_owned(SFL_K, Env e, int port, int h) {
   int4 sw = c_m.sw[c_m.port[port].w];
   SFL_NU
   for (int k = 0; k < sw.x; k++) {
@@ -430,10 +430,10 @@ SFL_FN void sem_delete_owned(Env e, int port, int h) {
 
 // rail_network.py:303-416 transition_semaphore, step by step
 template <class Env>
-SFL_FN void transition_semaphore(Env e, int source, int out_port, int target, int h, int now, int st, int old_next, int old_prev) {
+SFL_FN void transition_semaphore(SFL_K, Env e, int source, int out_port, int target, int h, int now, int st, int old_next, int old_prev) {
   if (st != ST_MALF) {                                                  // :315-323
-    sem_delete_owned(e, old_next, h);
-    if (old_prev >= 0) sem_delete_owned(e, old_prev, h);
+    sem_delete_owned(K, e, old_next, h);
+    if (old_prev >= 0) sem_delete_owned(K, e, old_prev, h);
   }
   if (Env::HOT_TAIL) {                                                        // staged table: load, test, store
     int4 r = e.sem()[out_port];                                           // :326-334
@@ -493,7 +493,7 @@ SFL_FN void transition_semaphore(Env e, int source, int out_port, int target, in
 
 // ------------------------------------------------------------------------------------------------ decision (first lane)
 template <class Env>
-SFL_FN int delay_at(Env e, int tgt_index, int cell, int dir, int now, int la) {
+SFL_FN int delay_at(SFL_K, Env e, int tgt_index, int cell, int dir, int now, int la) {
   int d = c_m.dist[((size_t)tgt_index * (c_m.Hp * c_m.Wp) + cell) * 4 + dir];
   if (d >= SFL_INF_DIST) { e.h()->err |= SFL_ERR_INF_DISTANCE; d = 0; }     // observer.py:35-36
   return now - la + d;                                                      // observer.py:41
@@ -502,9 +502,9 @@ SFL_FN int delay_at(Env e, int tgt_index, int cell, int dir, int now, int la) {
 // the tail of one iteration of distr_q.py:302-362 that must wait for the train ticks run inside env.step()
 // (switch_env.py:648-649): arrival flush (:345-356), interaction counter (:362), truncation (switch_env.py:652-657)
 template <int KIND, class Env>
-SFL_FN void finish_decision(Env e, const Hp hp, int env_id) {
+SFL_FN void finish_decision(SFL_K, Env e, const Hp hp, int env_id) {
   const bool TRACE = KIND == K_FULL;
-  const int mode = run_mode<KIND>();
+  const int mode = run_mode<KIND>(K);
   EnvHdr *h = e.h();
   if (mode == SFL_MODE_LEARN || mode == SFL_MODE_REPLAY) {
     unsigned long long fresh = h->done_mask & ~h->at_dest_mask;
@@ -517,7 +517,7 @@ SFL_FN void finish_decision(Env e, const Hp hp, int env_id) {
       SFL_NU
       for (int i = 0; i < n; i++) {
         int2 pe = e.pend()[t * c_L.pend_cap + i];
-        q_update(e, hp, (unsigned)pe.x, (pe.y >> 24) & 15, 1000.0, nullptr, (pe.y >> 12) & 0xFFF, -1);
+        q_update(K, e, hp, (unsigned)pe.x, (pe.y >> 24) & 15, 1000.0, nullptr, (pe.y >> 12) & 0xFFF, -1);
       }
       b.y &= 0xFFFF;
       e.trb()[t] = b;
@@ -546,7 +546,7 @@ SFL_FN void finish_decision(Env e, const Hp hp, int env_id) {
 // observation of train t at its active switch (observer.py:246-308 + switch_agents.py:104-134)
 struct Obs { int s, P, A, p0, a0, cur, semb, mask, ok; unsigned key; };
 template <class Env>
-SFL_FN Obs observe(Env e, int t, int now, const int4 ta, const int4 tb) {
+SFL_FN Obs observe(SFL_K, Env e, int t, int now, const int4 ta, const int4 tb) {
   Obs ob;
   ob.s = tb.y & 0xFFFF;
   const int4 sw = c_m.sw[ob.s];
@@ -562,7 +562,7 @@ SFL_FN Obs observe(Env e, int t, int now, const int4 ta, const int4 tb) {
   ob.ok = ob.cur >= 0 && ob.cur < ob.P;
   ob.key = 0u; ob.mask = 0;
   if (!ob.ok) return ob;
-  int delay = delay_at(e, tr0.w, ta.x, ta.y & 0xFF, now, tr1.y);
+  int delay = delay_at(K, e, tr0.w, ta.x, ta.y & 0xFF, now, tr1.y);
   int level = delay <= 0 ? 0 : (delay <= (tr1.y - tr1.x) * 20 ? 1 : 2);           // observer.py:239-244
   ob.key = (((unsigned)(ob.p0 + ob.cur) * c_L.NT + tr0.w) * 16u + semb) * 3u + level;
   const int4 px = c_m.pexit[ob.p0 + ob.cur];                                      // switch_agents.py:104-134
@@ -580,13 +580,13 @@ SFL_FN Obs observe(Env e, int t, int now, const int4 ta, const int4 tb) {
 
 // one switch-agent decision: observe (O1-O3) -> act (Q1) -> apply (E2, E3, R1) -> Q-update (Q2, Q3)
 template <int KIND, class Env>
-SFL_FN void decide(Env e, const Hp hp, int env_id, int t) {
+SFL_FN void decide(SFL_K, Env e, const Hp hp, int env_id, int t) {
   const bool TRACE = KIND == K_FULL;
-  const int mode = run_mode<KIND>();
+  const int mode = run_mode<KIND>(K);
   EnvHdr *h = e.h();
   const int now = h->elapsed;
   int4 ta = e.tra()[t], tb = e.trb()[t];
-  const Obs ob = observe(e, t, now, ta, tb);
+  const Obs ob = observe(K, e, t, now, ta, tb);
   if (!ob.ok) {
     // observer.py:294-307: "No train detected at active switch" -- the reference then dies on an unbound current_port
     // (:307).  There is nothing to be faithful to past this point: flag the env, abandon the episode, carry on.
@@ -615,7 +615,7 @@ SFL_FN void decide(Env e, const Hp hp, int env_id, int t) {
     }
     if (action < 0 || action >= A) { h->err |= SFL_ERR_BAD_ACTION; action = A - 1; }
     if (exploited) {
-      my_row = q_row(e, hp, key);
+      my_row = q_row(K, e, hp, key);
       if (max_action(my_row, A, mask) != action) h->err |= SFL_ERR_REPLAY_DIVERGED;
     }
   } else if (mode == SFL_MODE_LEARN) {
@@ -641,7 +641,7 @@ SFL_FN void decide(Env e, const Hp hp, int env_id, int t) {
     }
   }
   if (action < 0) {                                        // exploit (distr_q.py:318-319) / test() (:211)
-    my_row = q_row(e, hp, key);
+    my_row = q_row(K, e, hp, key);
     action = max_action(my_row, A, mask);
   }
   // ---- apply (switch_env.py:203-294, switch_agents.py:136-168)
@@ -655,7 +655,7 @@ SFL_FN void decide(Env e, const Hp hp, int env_id, int t) {
     int4 op = c_m.port[out_port];
     next_port = op.x;
     int old_prev = (tb.x & 0xFFFF) == 0xFFFF ? -1 : (tb.x & 0xFFFF);
-    transition_semaphore(e, in_port, out_port, next_port, t, now, st, my_port, old_prev);
+    transition_semaphore(K, e, in_port, out_port, next_port, t, now, st, my_port, old_prev);
     tb.x = (out_port & 0xFFFF) | (in_port << 16);                                 // prev_port = out, source_port = in
     ta.w = (ta.w & 0xFFFF) | (next_port << 16);
     next_switch = c_m.port[next_port].w;
@@ -680,10 +680,10 @@ SFL_FN void decide(Env e, const Hp hp, int env_id, int t) {
     SFL_NU
     for (int i = 0; i < pl; i++, pp >>= 4) {
       int a = pp & 0xF;
-      if (a != A_STOP) { Mv c = check_action(a, cell, d2); cell = c.cell; d2 = c.dir; }
+      if (a != A_STOP) { Mv c = check_action(K, a, cell, d2); cell = c.cell; d2 = c.dir; }
     }
   }
-  int curr = delay_at(e, tr0.w, cell, d2, now, tr1.y);
+  int curr = delay_at(K, e, tr0.w, cell, d2, now, tr1.y);
   int reward_out = tb.z - curr;
   if (!all_blocked && (plan & 0xFu) == A_STOP) reward_out -= 1300;
   e.rewards()[next_switch * c_L.T + t] = reward_out;                              // switch_env.py:289
@@ -704,8 +704,8 @@ SFL_FN void decide(Env e, const Hp hp, int env_id, int t) {
       const int prev_sw = (pe.y >> 12) & 0xFFF;
       // max_q creates the successor row (distr_q.py:463-465) -- but only when it is consulted: not for a train that
       // stayed at the same switch (:444-447)
-      if (prev_sw != s && !my_row) my_row = q_row(e, hp, key);
-      q_update(e, hp, (unsigned)pe.x, (pe.y >> 24) & 15, (double)reward_in, my_row, prev_sw, s);
+      if (prev_sw != s && !my_row) my_row = q_row(K, e, hp, key);
+      q_update(K, e, hp, (unsigned)pe.x, (pe.y >> 24) & 15, (double)reward_in, my_row, prev_sw, s);
       SFL_NU
       for (int j = hit; j + 1 < n; j++) pend[j] = pend[j + 1];
       n--;
@@ -734,6 +734,8 @@ SFL_FN void decide(Env e, const Hp hp, int env_id, int t) {
   }
   if (TRACE) h->last_next_sw = next_switch;
   h->decisions++;
+  if (mask == (1 << (A - 1))) h->forced_stops++;
+  if (action == A - 1) h->stop_actions++;
   h->pending_fin = s;
 }
 
@@ -741,7 +743,7 @@ SFL_FN void decide(Env e, const Hp hp, int env_id, int t) {
 // switch_env.py:93-158 with a constant map: state re-init + the precomputed _init_ports table (:507-568)
 // (`on`: this group resets; the syncs are the whole warp's)
 template <int G, class Env>
-SFL_NI void env_reset(Env e, const Grp<G> &g, int on) {
+SFL_NI void env_reset(SFL_K, Env e, const Grp<G> &g, int on) {
   EnvHdr *h = e.h();
   const int T = on ? c_L.T : 0, NP = on ? c_L.NP : 0;
   SFL_NU
@@ -798,7 +800,7 @@ SFL_FN int malf_stage2(const Hp hp, int now, int t) {
 template <int G, int KIND, bool ONE, class Env>
 // `live` = this group's environment takes part (not halted, not an idle slot of the last warp); every loop bound and
 // branch that contains a collective is warp-uniform, the per-group work inside is predicated.
-SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g, TickRegs &R, const int live) {
+SFL_FN void env_tick(SFL_K, Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g, TickRegs &R, const int live) {
   const bool TRACE = KIND == K_FULL;
   EnvHdr *h = e.h();
   const int Tw = c_L.T;                                                  // warp-uniform loop bound
@@ -845,10 +847,10 @@ SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g
     else {
       int pp = p, dd = d;
       if (p < 0) { const int4 tr0 = c_m.train0[t]; pp = tr0.x; dd = tr0.y; }
-      const unsigned me = mv_entry(pp, dd);
+      const unsigned me = mv_entry(K, pp, dd);
       if (pl == 0) a = A_FWD;
       else { a = plan & 0xF; prev_act = a; plan >>= 4; pl--; }
-      if (p >= 0) { Mv c = mv_apply(me, a, p); ecell = c.valid ? c.cell : p; flags = 1 | (c.valid ? 2 : 0); }
+      if (p >= 0) { Mv c = mv_apply(K, me, a, p); ecell = c.valid ? c.cell : p; flags = 1 | (c.valid ? 2 : 0); }
       // action preprocessing (a is never DO_NOTHING here: the reference always sends an action)
       act = a;
       if (st == ST_WAITING) act = A_NOTHING;
@@ -858,7 +860,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g
       const int upd = (mc == 0) && act != A_STOP;
       int ncell = p;
       if (p < 0) { if (saved) { ncell = pp; nd = dd; } }
-      else if (saved && upd) { Mv c = mv_apply(me, saved, p); if (c.valid) { ncell = c.cell; nd = c.dir; } act = saved; }
+      else if (saved && upd) { Mv c = mv_apply(K, me, saved, p); if (c.valid) { ncell = c.cell; nd = c.dir; } act = saved; }
       src = p >= 0 ? p : -1 - t;
       dst = ncell >= 0 ? ncell : src;
     }
@@ -970,7 +972,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g
       // _check_active_switch (switch_env.py:427-485)
       if (p >= 0 && nxt != ST_WAITING) {
         int peek = pl ? (int)(plan & 0xF) : A_FWD;
-        Mv c = check_action(peek, p, d);
+        Mv c = check_action(K, peek, p, d);
         int s = c_m.cell_switch[c.cell];
         if (s >= 0) {
           int ok = 1;
@@ -1064,7 +1066,7 @@ SFL_FN void env_tick(Env e, Scratch sc, const Hp hp, int env_id, const Grp<G> &g
 
 // ------------------------------------------------------------------------------------------------ episode end
 template <class Env>
-SFL_NI void episode_end(Env e, int env_id) {   // first lane
+SFL_NI void episode_end(SFL_K, Env e, int env_id) {   // first lane
   EnvHdr *h = e.h();
   if (c_ra.ep_log && h->n_ep_logged < c_ra.ep_cap) {
     sfl_ep_rec *rec = c_ra.ep_log + (size_t)env_id * c_ra.ep_cap + h->n_ep_logged;
@@ -1076,6 +1078,7 @@ SFL_NI void episode_end(Env e, int env_id) {   // first lane
       for (int t = 0; t < c_L.T; t++) d[t] = e.trb()[t].z;
     }
   }
+  h->arrived_trains += (unsigned)popc64(h->done_mask);
   h->n_ep_logged++;
   h->episode++;
   h->need_reset = 1;
@@ -1090,13 +1093,13 @@ SFL_NI void episode_end(Env e, int env_id) {   // first lane
 // The AEC protocol driven from the host (switch_env.py:616-666): report the waiting decision the way AECEnv.last()
 // would, or the end of the episode.  First lane of the group.
 template <class Env>
-SFL_FN void step_report(Env e, int env_id, int t) {
+SFL_FN void step_report(SFL_K, Env e, int env_id, int t) {
   EnvHdr *h = e.h();
   sfl_step_rec *o = c_ra.step_out + env_id;
   o->pending = 0; o->sw = -1; o->train = -1; o->key = 0u; o->mask = 0;
   if (t >= 0) {
     const int4 ta = e.tra()[t], tb = e.trb()[t];
-    const Obs ob = observe(e, t, h->elapsed, ta, tb);
+    const Obs ob = observe(K, e, t, h->elapsed, ta, tb);
     if (!ob.ok) { h->err |= SFL_ERR_NO_TRAIN_AT_SWITCH; h->aborted++; h->truncated = 1; }    // last() raises in the reference
     else {
       o->pending = 1; o->sw = ob.s; o->train = t; o->key = ob.key; o->mask = ob.mask;
@@ -1110,7 +1113,7 @@ SFL_FN void step_report(Env e, int env_id, int t) {
 }
 
 template <int G, int KIND, bool TH, bool SQ, bool ONE>
-SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
+SFL_FN void env_run(SFL_K, int env_id, unsigned stage, char *host_scratch) {
   const bool TRACE = KIND == K_FULL;
   const Grp<G> g;
   const int valid = env_id < c_ra.n_envs;                                 // idle slots of the last warp keep the warp's rendezvous
@@ -1120,6 +1123,7 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
   EnvT<TH, SQ> e;
   Hp hp;
   Scratch sc;
+  e.kp = &K; sc.kp = &K;
   e.gb = gbase;
 #if SFL_DEV
   {
@@ -1159,11 +1163,11 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
     R.active = h->active_mask; R.done = h->done_mask;
     need_reset = h->need_reset; live = !h->halted;
   }
-  const int stepping = TRACE && run_mode<KIND>() == SFL_MODE_STEP;
+  const int stepping = TRACE && run_mode<KIND>(K) == SFL_MODE_STEP;
   int paused = 0;                                                         // stepping: a decision waits for the host
   if (stepping) {
     if (live && g.gl == 0) {
-      if (h->cur_train >= 0) { decide<KIND>(e, hp, env_id, h->cur_train); h->cur_train = -1; }
+      if (h->cur_train >= 0) { decide<KIND>(K, e, hp, env_id, h->cur_train); h->cur_train = -1; }
       else h->last_next_sw = -1;
     }
     g.sync();
@@ -1177,21 +1181,21 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
     if (!(wf & 1u)) break;
     if (wf & 2u) {
       if (due && g.gl == 0 && stepping) {
-        if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<KIND>(e, hp, env_id);
+        if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<KIND>(K, e, hp, env_id);
         int t = -1;
         if (!(h->terminated || h->truncated) && h->active_mask) { t = ffs64(h->active_mask); h->active_mask &= h->active_mask - 1; }
-        step_report(e, env_id, t);
-        if (h->terminated || h->truncated) episode_end(e, env_id);
+        step_report(K, e, env_id, t);
+        if (h->terminated || h->truncated) episode_end(K, e, env_id);
       } else if (due && g.gl == 0) {
         SFL_NU
         for (;;) {                                                        // agent_iter: FIFO in train-handle order
-          if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<KIND>(e, hp, env_id);
+          if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<KIND>(K, e, hp, env_id);
           if (h->terminated || h->truncated || !h->active_mask) break;
           int t = ffs64(h->active_mask);
           h->active_mask &= h->active_mask - 1;
-          decide<KIND>(e, hp, env_id, t);
+          decide<KIND>(K, e, hp, env_id, t);
         }
-        if (h->terminated || h->truncated) episode_end(e, env_id);
+        if (h->terminated || h->truncated) episode_end(K, e, env_id);
       }
       g.sync();
       if (due) { need_reset = h->need_reset; R.active = 0; if (stepping) paused = h->cur_train >= 0; }
@@ -1200,11 +1204,11 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
     if (any_reset) {
       if (live && need_reset && hp->episodes >= 0 && h->episode >= hp->episodes) live = 0;      // halt: need_reset stays set
       const int on = live && need_reset;
-      env_reset<G>(e, g, on);
+      env_reset<G>(K, e, g, on);
       if (on) { need_reset = 0; R.elapsed = 0; R.ended = 0; R.rng_blk = -1; R.active = 0; R.done = 0; }
       any_reset = 0;
     }
-    env_tick<G, KIND, ONE>(e, sc, hp, env_id, g, R, live && !paused);
+    env_tick<G, KIND, ONE>(K, e, sc, hp, env_id, g, R, live && !paused);
   }
   g.sync();
   if (valid && g.gl == 0) {
@@ -1215,6 +1219,7 @@ SFL_FN void env_run(int env_id, unsigned stage, char *host_scratch) {
     c->err = h->err; c->q_rows = h->q_rows; c->halted = h->halted; c->n_dec_logged = h->n_dec_logged;
     c->n_tick_logged = h->n_tick_logged; c->n_ep_logged = h->n_ep_logged; c->elapsed = h->elapsed;
     c->aborted = h->aborted; c->reserved = 0;
+    c->forced_stops = h->forced_stops; c->stop_actions = h->stop_actions; c->arrived_trains = h->arrived_trains; c->reserved2 = 0;
   }
 #if SFL_DEV
   g.sync();

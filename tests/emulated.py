@@ -50,6 +50,7 @@ class EmulEngine(backend.Engine):
 
     def _upload(self, name, host):
         raw = np.ascontiguousarray(host).view(np.uint8).reshape(-1)
+        self.h2d_bytes += raw.size
         self.buf[name][:raw.size].copy_(self.torch.from_numpy(raw))
 
     def _download(self, name, nbytes=None):

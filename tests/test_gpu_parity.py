@@ -304,42 +304,116 @@ def test_cuda_distance_map_large_grid_uses_the_global_memory_variant():
         assert np.array_equal(d[k], railmap.distance_to(fx["grid"], (int(r), int(c)))), k
 
 
-@pytest.mark.parametrize("name,lanes", [("c1_synth18", None), ("c1_synth18", 1), ("slips24_t6", None), ("slips24_t6", 4),
-                                        ("synth40_t12", 8), ("c4_synth100_t50", None)])
-def test_cuda_production_kernels_equal_the_full_kernel(name, lanes):
-    """The learn / greedy kernels are compile-time specialisations (no trace, no replay, single-pass train loops when
-    T <= lanes).  Free-running learn and a greedy rollout through them must give exactly what the full kernel -- the one
-    the replay tests pin against the reference -- gives for the same seeds: counters, episode logs, Q-tables."""
-    fx, _ = load_golden(name)
-    rm = backend.RailMap(fx)
-    hp = dict(gamma=0.95, epsilon=0.5, epsilon_decay_rate=0.999, lr=0.2, lr_decay_rate=0.9999, default_q=1.0)
-    B, n_ep = 6, 3
+# (fixture, lanes, roomy): the small-batch configurations whose kernel instantiations are pinned below.  The last rows are
+# the instantiations bench.py launches at full size (C2: 4096 envs -> G=16 / ONE / TH; C3: 4096 envs per map -> G=16,
+# ROOMY; C4: 8192 envs -> G=32, not roomy); test_cuda_bench_kernel_variants_are_parity_tested checks that they really are.
+VARIANT_CASES = [("c1_synth18", None, None), ("c1_synth18", 1, None), ("slips24_t6", None, None), ("slips24_t6", 4, None),
+                 ("synth40_t12", 8, None), ("c4_synth100_t50", None, None),
+                 ("c1_synth18", 16, None), ("c3_rail80_s64", 16, True), ("c3_rail80_s64", 16, False),
+                 ("c4_rail100_t50", 32, False), ("c4_rail100_t50", 32, True)]
+HP_VARIANT = dict(gamma=0.95, epsilon=0.5, epsilon_decay_rate=0.999, lr=0.2, lr_decay_rate=0.9999, default_q=1.0)
 
-    def run(full):
-        eng = gpu_engine(rm, n_envs=B, q_cap=32768 if "c4" in name else 4096, ep_cap=8, lanes=lanes,
-                         dec_cap=4 if full else 0, tick_cap=0)
-        eng.set_hparams(**hp, seeds=np.arange(B) + 77, episodes=n_ep)
-        eng.reset()
-        eng.enable_q_init(True)
-        eng.run(backend.MODE_LEARN, 1_000_000)
-        eng.check_errors(allow=backend.ERR_NO_TRAIN_AT_SWITCH)
-        c1 = eng.counters().copy()
-        _, log1, d1 = eng.episode_log()
-        eng.set_hparams(**hp, seeds=np.arange(B) + 77, episodes=1, episode_base=n_ep)
-        eng.reset(keep_q=True, keep_interactions=True)
-        eng.run(backend.MODE_GREEDY, 1_000_000)
-        eng.check_errors(allow=backend.ERR_NO_TRAIN_AT_SWITCH)
-        c2 = eng.counters().copy()
-        _, log2, d2 = eng.episode_log()
-        q = [eng.export_q(i) for i in range(B)]
-        eng.close()
-        return c1, log1[:, :n_ep].copy(), d1[:, :n_ep].copy(), c2, log2[:, :1].copy(), d2[:, :1].copy(), q
 
-    a, b = run(full=True), run(full=False)
+def _variant_run(rm, cls, name, lanes, roomy, full, B=6, n_ep=3, **extra):
+    """Free-running learn (n_ep episodes) then one greedy rollout; returns everything observable + the kernel names."""
+    eng = cls(rm, n_envs=B, q_cap=32768 if "c4" in name else 4096, ep_cap=8, lanes=lanes, roomy=roomy,
+              dec_cap=4 if full else 0, tick_cap=0, **extra)
+    kernels = (eng.kernel_variant(backend.MODE_LEARN, traced=full), eng.kernel_variant(backend.MODE_GREEDY, traced=full))
+    eng.set_hparams(**HP_VARIANT, seeds=np.arange(B) + 77, episodes=n_ep)
+    eng.reset()
+    eng.enable_q_init(True)
+    eng.run(backend.MODE_LEARN, 1_000_000)
+    eng.check_errors(allow=backend.ERR_NO_TRAIN_AT_SWITCH)
+    c1 = eng.counters().copy()
+    _, log1, d1 = eng.episode_log()
+    eng.set_hparams(**HP_VARIANT, seeds=np.arange(B) + 77, episodes=1, episode_base=n_ep)
+    eng.reset(keep_q=True, keep_interactions=True)
+    eng.run(backend.MODE_GREEDY, 1_000_000)
+    eng.check_errors(allow=backend.ERR_NO_TRAIN_AT_SWITCH)
+    c2 = eng.counters().copy()
+    _, log2, d2 = eng.episode_log()
+    q = [eng.export_q(i) for i in range(B)]
+    eng.close()
+    return (c1, log1[:, :n_ep].copy(), d1[:, :n_ep].copy(), c2, log2[:, :1].copy(), d2[:, :1].copy(), q), kernels
+
+
+def _assert_same_run(a, b):
     for k in ("decisions", "ticks", "train_ticks", "episodes", "err", "q_rows", "aborted"):
         assert np.array_equal(a[0][k], b[0][k]) and np.array_equal(a[3][k], b[3][k]), k
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
     assert a[6] == b[6]
+
+
+@pytest.mark.parametrize("name,lanes,roomy", VARIANT_CASES)
+def test_cuda_production_kernels_equal_the_full_kernel_and_the_host_build(name, lanes, roomy):
+    """The learn / greedy kernels are compile-time specialisations (no trace, no replay, single-pass train loops when
+    T <= lanes, the 4-CTA "roomy" build).  Free-running learn and a greedy rollout through them must give exactly what
+    (a) the full kernel -- the one the replay tests pin against the reference -- and (b) the same sources compiled for the
+    host (tests/emul, which the CPU suite pins against the reference too) give for the same seeds: counters, episode
+    logs, Q-tables."""
+    from tests.emulated import EmulEngine
+    fx, _ = load_golden(name)
+    rm = backend.RailMap(fx)
+    prod, k_prod = _variant_run(rm, backend.Engine, name, lanes, roomy, full=False)
+    full, k_full = _variant_run(rm, backend.Engine, name, lanes, roomy, full=True)
+    assert "KIND=learn" in k_prod[0] and "KIND=greedy" in k_prod[1] and "KIND=full" in k_full[0], (k_prod, k_full)
+    if roomy is not None and lanes is not None and lanes >= 16 and "TH=0" in k_prod[0]:
+        assert f"ROOMY={int(roomy)}" in k_prod[0], k_prod
+    _assert_same_run(prod, full)
+    host, _ = _variant_run(rm, EmulEngine, name, None, None, full=False)
+    _assert_same_run(prod, host)
+
+
+def _bench_variants():
+    """Kernel instantiation of every bench.py workload at its full batch size (context only, no buffers)."""
+    import bench
+    out = {}
+    for wl, (fixture, envs, q_cap, _) in bench.WORKLOADS.items():
+        fxs = bench.workload_fixtures(bench.fixture_path(fixture))
+        per_map = envs // len(fxs)
+        eng = backend.Engine(backend.RailMap(fxs[0]), n_envs=per_map, q_cap=q_cap, ep_cap=4, shared_q=(wl == "c5"), bind=False)
+        out[wl] = eng.kernel_variant(backend.MODE_LEARN)
+        eng.close()
+    return out
+
+
+def test_cuda_bench_kernel_variants_are_parity_tested():
+    """Every k_run instantiation bench.py times is one of the instantiations the parity tests above run (same template
+    arguments; grid / block size are launch parameters, not code)."""
+    tested = set()
+    for name, lanes, roomy in VARIANT_CASES:
+        fx, _ = load_golden(name)
+        eng = backend.Engine(backend.RailMap(fx), n_envs=6, q_cap=4096, ep_cap=8, lanes=lanes, roomy=roomy, bind=False)
+        tested.add(eng.kernel_variant(backend.MODE_LEARN))
+        eng.close()
+    fx, _ = load_golden("c4_rail100_t50")
+    sq = backend.Engine(backend.RailMap(fx), n_envs=6, q_cap=2, shared_q=True, bind=False)        # pinned by the shared-table test below
+    tested.add(sq.kernel_variant(backend.MODE_LEARN))
+    sq.close()
+    for wl, variant in _bench_variants().items():
+        assert variant in tested, (wl, variant, sorted(tested))
+
+
+def test_cuda_shared_table_kernel_equals_the_host_build_on_the_c4_map():
+    """The SQ instantiation bench.py --workload c5 launches (large map, tail in HBM): integer accumulation makes the
+    device run bit-reproducible, so it must equal the host build of the same sources exactly."""
+    from tests.emulated import EmulEngine
+    fx, _ = load_golden("c4_rail100_t50")
+    rm = backend.RailMap(fx)
+    hp = dict(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0)
+    out = []
+    for cls in (backend.Engine, EmulEngine):
+        eng = cls(rm, n_envs=5, q_cap=2, ep_cap=4, shared_q=True)
+        eng.set_hparams(**hp, seeds=np.arange(5) + 3, episodes=-1)
+        eng.reset()
+        eng.init_shared_q(0.0)
+        for _ in range(4):
+            eng.run(backend.MODE_LEARN, 128)
+            eng.check_errors()
+            eng.shared_q_sync()
+        out.append((eng.shared_q_table(), eng.counters()["decisions"].copy()))
+        eng.close()
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][0], out[1][0])
 
 
 @pytest.mark.parametrize("name", ["c1_synth18", "slips24_t6"])

@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol(product_lib):
     assert {"sfl_create", "sfl_run", "sfl_reset", "sfl_bind", "sfl_export_q", "sfl_import_q", "sfl_query_sizes"} <= set(names)
     for n in names:
         assert hasattr(product_lib, n), f"{n} declared in include/switchfl_b200.h but not exported"
-    assert product_lib.sfl_abi_version() == 4
+    assert product_lib.sfl_abi_version() == backend.ABI_VERSION
 
 
 def test_struct_layouts_match_the_header():
