@@ -274,7 +274,7 @@ def run_block(cx: Ctx, wl: str, args, steps: int, warmup: int, sampler=None, flu
     def seeds_of(k):
         return np.arange(Bp, dtype=np.uint64) + np.uint64(SEED + cx.rank * B + k * Bp)
 
-    rms = [backend.RailMap(fx) for fx in fxs]
+    rms = [backend.RailMap(fx, device_bfs=cx.local) for fx in fxs]      # distance maps on the GPU (sfl_distance_map)
     engs = [backend.Engine(rm, n_envs=Bp, device=cx.dev, q_cap=q_cap, ep_cap=4, shared_q=shared, **kw) for rm in rms]
     for k, eng in enumerate(engs):
         eng.set_hparams(**HP, seeds=seeds_of(k), episodes=-1)

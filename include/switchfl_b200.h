@@ -218,6 +218,11 @@ int sfl_describe_launch(void *ctx, int mode, int traced, char *buf, int cap);
 /* enable the optimistic initialisation of distr_q.py:299-300 for rows created from now on           */
 int sfl_enable_q_init(void *ctx, int on);
 
+/* __init_q_table runs at the first episode of EVERY learn() call and ASSIGNS its rows (distr_q.py:299-300, 156-158, 179-181):
+ * overwrite, in every environment's table, the rows of optimistic-init states that already exist (an earlier learn(),
+ * load() or test() created them) with their initial values.  Device-side; uses the bound hparams (default_q).            */
+int sfl_reapply_q_init(void *ctx, void *stream);
+
 /* advance every env by up to max_ticks flatland ticks (all decisions in between included);
  * replaces the loop body of DistrQLearning.learn / test  (distr_q.py:302-362, 199-224)               */
 int sfl_run(void *ctx, int mode, int max_ticks, void *stream);

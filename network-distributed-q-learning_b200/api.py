@@ -265,16 +265,20 @@ class DistrQLearning:
         return c
 
     def _apply_q_init_to_existing_rows(self):
-        """distr_q.py:156-158,179-181 ASSIGN the initial rows at t == 0, overwriting whatever load()/test() put there."""
+        """distr_q.py:156-158,179-181 ASSIGN the initial rows at t == 0, overwriting whatever an earlier learn() / load() /
+        test() put there (on the device, for all environments at once)."""
         eng = self.env.engine
-        for i in range(self.env.n_envs):
-            init_rows = self.env.rail_map.q_init_rows(self._default_q_of(i))
-            q = eng.export_q(i)
-            hit = [k for k in q if k in init_rows]
-            if hit:
-                for k in hit:
-                    q[k] = list(init_rows[k])
-                eng.import_q(i, q)
+        if not eng.shared_q:
+            eng.reapply_q_init()
+            return
+        q = eng.shared_q_table()                                          # shared-table mode: the one dense table, on the host
+        tr = self.env.rail_map.trains
+        port, tgt = np.nonzero(np.asarray(tr.qinit_act) >= 0)
+        act, val = np.asarray(tr.qinit_act)[port, tgt], np.asarray(tr.qinit_val)[port, tgt]
+        for semb in range(1, 16):
+            q[port, tgt, semb, :, :] = self._default_q_of(0)
+            q[port, tgt, semb, :, act] = val[:, None]
+        eng._upload("shared_q", q)
 
     def learn_chunk(self, max_ticks: Optional[int] = None) -> np.ndarray:
         """Streaming API: upload the per-env hyper-parameter block, advance every environment by up to ``max_ticks``

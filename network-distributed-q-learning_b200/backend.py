@@ -86,6 +86,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sfl_bind.argtypes = [C.c_void_p, C.POINTER(Buffers)]
     lib.sfl_reset.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.sfl_enable_q_init.argtypes = [C.c_void_p, C.c_int]
+    lib.sfl_reapply_q_init.argtypes = [C.c_void_p, C.c_void_p]
     lib.sfl_set_lanes.argtypes = [C.c_void_p, C.c_int]
     lib.sfl_get_lanes.argtypes = [C.c_void_p]
     lib.sfl_set_cta_warps.argtypes = [C.c_void_p, C.c_int]
@@ -366,6 +367,11 @@ class Engine:
     def lanes(self) -> int:
         """Lanes of a warp cooperating on one environment (a scheduling choice; results do not depend on it)."""
         return int(self.lib.sfl_get_lanes(self.ctx))
+
+    def reapply_q_init(self):
+        """Overwrite the existing rows of optimistic-init states with their initial values in every environment's table
+        (``sfl_reapply_q_init``: what __init_q_table does to a non-empty table, distr_q.py:156-158, 179-181)."""
+        self._ck(self.lib.sfl_reapply_q_init(self.ctx, self._stream()))
 
     def describe_launch(self, mode: int = MODE_LEARN, traced: bool = False) -> str:
         """The kernel instantiation + launch configuration ``run(mode)`` would use (``sfl_describe_launch``)."""

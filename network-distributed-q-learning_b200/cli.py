@@ -35,7 +35,11 @@ def fixture_from_env_section(env: Dict[str, str], seed: int) -> dict:
     if int(env["height"]) != n:
         raise ValueError("the reference only works on square grids (utils/rail_graph.py:43-48)")
     cities = int(env.get("max_num_cities", 2))
-    chords = max(2, cities * int(env.get("max_rails_between_cities", 1)) * int(env.get("max_rail_pairs_in_city", 1)) // 2)
+    rails = int(env.get("max_rails_between_cities", 1))
+    if rails >= 2:            # double track between the cities (hyperparam_tuning.py:20): the right-hand-running generator
+        lines = max(2, min(cities // 3, n // 8))
+        return mapgen.rail_fixture(n, int(env["number_of_agents"]), seed, n_rings=2, n_lines=lines, cross_every=10, num_cities=cities)
+    chords = max(2, cities * rails * int(env.get("max_rail_pairs_in_city", 1)) // 2)
     return mapgen.make_fixture(n=n, n_trains=int(env["number_of_agents"]), n_chords=chords, seed=seed, num_cities=cities)
 
 

@@ -107,7 +107,33 @@ SFL_FN void env_init(const InitArgs &ia, int env_id, int lane, int lanes) {
   }
 }
 
+// distr_q.py:299-300 runs __init_q_table at the first episode of EVERY learn() call and ASSIGNS its rows (:156-158, :179-181):
+// rows of optimistic-init states that already exist (an earlier learn(), load() or test() created them) are overwritten with
+// the initial values; rows that do not exist yet are materialised lazily with the same values on first touch.
+struct ReinitArgs { Layout L; RO<int4> sw, port; RO<int8_t> qinit; char *state; const sfl_hparams *hp; int n_envs, pad; };
+SFL_FN void q_reinit_slot(const ReinitArgs &a, int env, int slot) {
+  double *row = (double *)(a.state + (size_t)env * a.L.env_stride + a.L.off_q) + (size_t)slot * a.L.q_stride;
+  const unsigned long long k = *(const unsigned long long *)row;
+  if (!k) return;
+  const unsigned key = (unsigned)(k - 1ull), per_port = (unsigned)(a.L.NT * 48);
+  const int port = (int)(key / per_port);
+  const unsigned rem = key - (unsigned)port * per_port;
+  const int tgt = (int)(rem / 48u), semb = (int)((rem % 48u) / 3u);
+  const int qi = a.qinit[port * a.L.NT + tgt];
+  if (qi < 0 || semb == 0) return;
+  const int A = a.sw[a.port[port].w].y;
+  const double dq = a.hp[env].default_q;
+  for (int x = 0; x < A; x++) row[1 + x] = dq;
+  row[1 + (qi & 15)] = (qi & 16) ? 1000.0 : 500.0;
+}
+
 #ifndef SFL_HOST_EMUL
+__global__ void __launch_bounds__(256) k_q_reinit(const __grid_constant__ ReinitArgs a) {
+  const size_t n = (size_t)a.n_envs * a.L.q_cap;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    q_reinit_slot(a, (int)(i / a.L.q_cap), (int)(i % a.L.q_cap));
+}
+
 __global__ void __launch_bounds__(SFL_CTA_THREADS) k_init(const __grid_constant__ InitArgs ia) {
   int env_id = blockIdx.x * SFL_WARPS_PER_CTA + (threadIdx.x >> 5);
   if (env_id < ia.n_envs) env_init(ia, env_id, threadIdx.x & 31, 32);
@@ -601,6 +627,25 @@ int sfl_reset(void *ctx, int keep, void *stream) {
   CU(cudaGetLastError());
 #else
   for (int i = 0; i < c->cfg.n_envs; i++) env_init(ia, i, 0, 1);
+#endif
+  return SFL_OK;
+}
+
+int sfl_reapply_q_init(void *ctx, void *stream) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c) return fail(SFL_E_ARG, "null ctx%s");
+  if (!c->bound) return fail(SFL_E_STATE, "sfl_bind first%s");
+  if (c->cfg.shared_q) return fail(SFL_E_STATE, "shared-table mode keeps no per-environment tables%s");
+  DeviceGuard dg(c->device);
+  ReinitArgs a;
+  a.L = c->L; a.sw = c->m.sw; a.port = c->m.port; a.qinit = c->m.qinit; a.state = (char *)c->bufs.state;
+  a.hp = (const sfl_hparams *)c->bufs.hparams; a.n_envs = c->cfg.n_envs; a.pad = 0;
+#ifndef SFL_HOST_EMUL
+  k_q_reinit<<<c->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(a);
+  CU(cudaGetLastError());
+#else
+  (void)stream;
+  for (int e = 0; e < a.n_envs; e++) for (int i = 0; i < a.L.q_cap; i++) q_reinit_slot(a, e, i);
 #endif
   return SFL_OK;
 }

@@ -78,14 +78,17 @@ def _load_vendored_distance_map():
     return mod
 
 
-def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, inject=None, verbose=True):
+def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, inject=None, verbose=True, rail_env=None):
+    """``rail_env``: a ready RailEnv to run the reference on (tools/record_flatland_fixture.py passes a GENUINE flatland
+    one); default: the fixture-backed stand-in of oracle/trainsim.py."""
     import logging
     logging.disable(logging.INFO)
     from switchfl.distr_q import DistrQLearning
     from switchfl.switch_env import ASyncSwitchEnv
     from switchfl.utils.naming import name2switch_id
 
-    rail_env = trainsim.RailEnv(fx)
+    if rail_env is None:
+        rail_env = trainsim.RailEnv(fx)
     if inject is not None:
         rail_env.injected_malfunctions = dict(inject)         # the same schedule in every episode (replay input)
     env = ASyncSwitchEnv(rail_env, render_mode=None, max_steps=100_000)
@@ -203,7 +206,6 @@ def run_fixture(fx: dict, seed: int, n_episodes: int, hp: dict, inject=None, ver
         return r
 
     def traced_step(action):
-        n_ev = len(rail_env.malfunction_events)
         post = orig_step(action)
         o = np.full(18, -9, np.int64); o[:len(pending["obs"])] = pending["obs"]
         m = np.full(9, -1, np.int8); m[:len(pending["mask"])] = pending["mask"]

@@ -305,3 +305,35 @@ def test_emul_reference_loop_with_the_drop_in_learner_methods(emul_lib):
     assert model.q_table == q_dict(g["q_keys"], g["q_vals"])
     assert model.eval(g["dec_obs"][0][g["dec_obs"][0] != -9], 0, env.possible_agents[int(g["dec_switch"][0])]) == \
         q_dict(g["q_keys"], g["q_vals"])[tuple(int(x) for x in g["dec_obs"][0] if x != -9)][0]
+
+
+def check_reapply_q_init(engine_cls):
+    """A second learn() call re-runs __init_q_table (distr_q.py:299-300), which ASSIGNS the optimistic rows (:156-158,
+    :179-181): existing rows of init states go back to their initial values, every other row stays."""
+    import numpy as np
+    from tests._util import load_golden
+    fx, _ = load_golden("slips24_t6")
+    rm = backend.RailMap(fx)
+    eng = engine_cls(rm, n_envs=3, q_cap=4096, ep_cap=8)
+    eng.set_hparams(gamma=0.95, epsilon=0.5, epsilon_decay_rate=0.999, lr=0.2, lr_decay_rate=1.0, default_q=[1.5, -2.0, 0.25], seeds=[4, 5, 6], episodes=5)
+    eng.reset()
+    eng.enable_q_init(True)
+    eng.run(backend.MODE_LEARN, 100000)
+    eng.check_errors(allow=backend.ERR_NO_TRAIN_AT_SWITCH)
+    before = [eng.export_q(i) for i in range(3)]
+    eng.reapply_q_init()
+    for i, dq in enumerate([1.5, -2.0, 0.25]):
+        init = rm.q_init_rows(dq)
+        after = eng.export_q(i)
+        assert set(after) == set(before[i])
+        changed = 0
+        for k, row in before[i].items():
+            want = init[k] if k in init else row
+            assert after[k] == want, (i, k)
+            changed += want != row
+        assert changed > 0, "no learned init-state row to reset: the case is vacuous"
+    eng.close()
+
+
+def test_emul_reapply_q_init(emul_lib):
+    check_reapply_q_init(EmulEngine)

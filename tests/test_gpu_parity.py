@@ -443,3 +443,8 @@ def test_cuda_free_running_learn_equals_the_host_build(name):
     for k in ("decisions", "ticks", "train_ticks", "episodes", "err", "q_rows", "aborted"):
         assert np.array_equal(c1[k], c2[k]), k
     assert np.array_equal(l1, l2) and np.array_equal(d1, d2) and q1 == q2
+
+
+def test_cuda_reapply_q_init():
+    from tests.test_emul_parity import check_reapply_q_init
+    check_reapply_q_init(backend.Engine)

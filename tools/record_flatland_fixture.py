@@ -14,8 +14,12 @@ turns every "[UPSTREAM-UNVERIFIED]" row of SURVEY.md Appendix B into a pinned on
 """
 import argparse
 import configparser
+import os
+import sys
 
 import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def build_rail_env(cfg):
@@ -52,17 +56,39 @@ def fixture_of(rail_env, cfg, seed):
     }
 
 
+def save_fixture(path, fx):
+    np.savez_compressed(path, **{k: (np.array(v) if not isinstance(v, np.ndarray) else v) for k, v in fx.items()})
+
+
+def record_trace(rail_env, fx, cfg, seed, episodes):
+    """Run the reference's own learn() on ``rail_env`` with the tracing hooks of oracle/gen_golden.py (the reference
+    repository must be importable as ``switchfl``) and return the golden-vector dict."""
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    from oracle import gen_golden
+    m = cfg["MODEL"]
+    hp = dict(gamma=float(m["gamma"]), epsilon=float(m["epsilon"]), epsilon_decay_rate=float(m["epsilon_decay_rate"]), lr=float(m["lr"]),
+              lr_decay_rate=float(m["lr_decay_rate"]), default_q=float(m["default_q"]))
+    return gen_golden.run_fixture(fx, seed, episodes, hp, verbose=False, rail_env=rail_env)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", required=True, help="the reference's config.ini (hyperparam_tuning.py:51-78)")
     ap.add_argument("--out", required=True)
+    ap.add_argument("--trace", default=None, help="also record a golden-vector trace of the reference's learn() into this .npz")
+    ap.add_argument("--episodes", type=int, default=3, help="episodes of the recorded trace")
     args = ap.parse_args()
     cfg = configparser.ConfigParser()
     cfg.read(args.config)
     rail_env, seed = build_rail_env(cfg)
     fx = fixture_of(rail_env, cfg, seed)
-    np.savez_compressed(args.out, **{k: (np.array(v) if not isinstance(v, np.ndarray) else v) for k, v in fx.items()})
+    save_fixture(args.out, fx)
     print(f"wrote {args.out}: grid {fx['grid'].shape}, {len(fx['init_dir'])} trains, max_episode_steps {fx['max_episode_steps']}")
+    if args.trace:
+        out = record_trace(rail_env, fx, cfg, seed, args.episodes)
+        np.savez_compressed(args.trace, **out)
+        print(f"wrote {args.trace}: {len(out['dec_ep'])} decisions, {len(out['tick_ep'])} ticks")
 
 
 if __name__ == "__main__":
