@@ -21,7 +21,7 @@
 #if defined(__CUDACC__) && !defined(SFL_HOST_EMUL)
 #define SFL_DEV 1
 #define SFL_FN __device__ __forceinline__
-#define SFL_NI __device__ __noinline__
+#define SFL_NI __device__ __forceinline__
 #define SFL_CONST __constant__
 #define SFL_NU _Pragma("unroll 1")
 #define SFL_U4 _Pragma("unroll 4")
@@ -80,7 +80,6 @@ template <int G> struct Grp {
 SFL_FN int popc64(unsigned long long v) { return __popcll(v); }
 SFL_FN int ffs64(unsigned long long v) { return __ffsll((long long)v) - 1; }
 SFL_FN int popc32(unsigned v) { return __popc(v); }
-SFL_FN int clz32(unsigned v) { return __clz((int)v); }
 SFL_FN double dmul(double a, double b) { return __dmul_rn(a, b); }
 SFL_FN double dadd(double a, double b) { return __dadd_rn(a, b); }
 template <class T> SFL_FN T ldg(const T *p) { return __ldg(p); }
@@ -97,7 +96,6 @@ template <int G> struct Grp {
 SFL_FN int popc64(unsigned long long v) { return __builtin_popcountll(v); }
 SFL_FN int ffs64(unsigned long long v) { return __builtin_ffsll((long long)v) - 1; }
 SFL_FN int popc32(unsigned v) { return __builtin_popcount(v); }
-SFL_FN int clz32(unsigned v) { return v ? __builtin_clz(v) : 32; }
 SFL_FN double dmul(double a, double b) { volatile double r = a * b; return r; }
 SFL_FN double dadd(double a, double b) { volatile double r = a + b; return r; }
 template <class T> SFL_FN T ldg(const T *p) { return *p; }
@@ -323,63 +321,39 @@ SFL_FN int port_blocked(Env e, int next_port, int out_port, int me, int now) {
 // Row = [key+1 as u64 bits | A_max doubles]; open addressing, linear probing, no deletion.  A row is created
 // exactly where the reference's __check_entry (distr_q.py:47-57) would insert a dict entry, so the exported
 // key set equals the reference's.
-//
-// The decision phase runs GROUP-UNIFORM: every lane of the environment's group executes it with the same values (one
-// SIMT instruction stream either way), side effects are the first lane's, and the gathers -- semaphore records of the
-// ports around the switch, Q-row probes, the pending list -- are spread over the lanes and combined with votes.  A
-// group that has nothing to decide walks through with `on` false; every vote / sync is the whole warp's.
-//
-// q_find: the lanes probe PW consecutive slots of the chain at once (one round trip for chains up to PW long).
-template <int G, class Env>
-SFL_NI double *q_find(SFL_K, Env e, const Grp<G> &g, const Hp hp, const int on, const unsigned key) {
-  if (Env::SQ) return on ? c_ra.sq_q + (size_t)key * c_L.a_max : nullptr;       // shared-table mode: dense, initialised by the host
-  const int PW = G >= 4 ? 4 : G;
-  const unsigned mask = (unsigned)c_L.q_cap - 1u;
-  const unsigned i0 = (key * 2654435761u) >> 7;
-  EnvHdr *h = e.h();
-  const int q_rows = on ? h->q_rows : 0;
-  double *found = nullptr;
-  int done = !on, probe = 0;
+template <class Env>
+SFL_NI double *q_row(SFL_K, Env e, const Hp hp, unsigned key) {
+  if (Env::SQ) return c_ra.sq_q + (size_t)key * c_L.a_max;              // shared-table mode: dense, initialised by the host
+  unsigned mask = (unsigned)c_L.q_cap - 1u;
+  unsigned i = (key * 2654435761u) >> 7;
   SFL_NU
-  while (g.wany(!done)) {
-    unsigned long long k = 1ull;                                         // neither a match nor an empty slot
-    if (!done && g.gl < PW) k = *(const unsigned long long *)(e.q() + (size_t)((i0 + probe + g.gl) & mask) * c_L.q_stride);
-    const unsigned m = g.ballot(k == (unsigned long long)key + 1ull), z = g.ballot(k == 0ull);
-    if (!done) {
-      const unsigned mz = (m | z) & ((1u << PW) - 1u);
-      if (mz) {
-        const int f = ffs64(mz);
-        double *row = e.q() + (size_t)((i0 + probe + f) & mask) * c_L.q_stride;
-        if ((m >> f) & 1u) found = row + 1;
-        else if (q_rows >= c_L.q_cap - 1) { if (g.gl == 0) h->err |= SFL_ERR_Q_FULL; found = e.q() + 1; }   // keep running on row 0 (flagged)
-        else {
-          if (g.gl == 0) {                                               // the first empty slot of the chain: insert
-            *(unsigned long long *)row = (unsigned long long)key + 1ull;
-            h->q_rows = q_rows + 1;
-            const unsigned per_port = (unsigned)(c_L.NT * 48);
-            const int port = (int)(key / per_port);
-            const int A = c_m.sw[c_m.port[port].w].y;
-            const double dq = hp->default_q;
-            SFL_NU
-            for (int a = 0; a < A; a++) row[1 + a] = dq;
-            if (c_ra.q_init_on) {                                   // distr_q.py:81-181 (lazy: same values, created on first touch)
-              const unsigned rem = key - (unsigned)port * per_port;
-              const int tgt = (int)(rem / 48u), semb = (int)((rem % 48u) / 3u);
-              const int qi = c_m.qinit[port * c_L.NT + tgt];
-              if (qi >= 0 && semb != 0) row[1 + (qi & 15)] = (qi & 16) ? 1000.0 : 500.0;
-            }
-          }
-          found = row + 1;
-        }
-        done = 1;
-      } else {
-        probe += PW;
-        if (probe >= c_L.q_cap) { if (g.gl == 0) h->err |= SFL_ERR_Q_FULL; found = e.q() + 1; done = 1; }
+  for (int probe = 0; probe < c_L.q_cap; probe++) {
+    i &= mask;
+    double *row = e.q() + (size_t)i * c_L.q_stride;
+    unsigned long long k = *(unsigned long long *)row;
+    if (k == (unsigned long long)key + 1ull) return row + 1;
+    if (k == 0ull) {
+      if (e.h()->q_rows >= c_L.q_cap - 1) break;
+      *(unsigned long long *)row = (unsigned long long)key + 1ull;
+      e.h()->q_rows++;
+      unsigned per_port = (unsigned)(c_L.NT * 48);
+      int port = (int)(key / per_port);
+      int A = c_m.sw[c_m.port[port].w].y;
+      double dq = hp->default_q;
+      SFL_NU
+      for (int a = 0; a < A; a++) row[1 + a] = dq;
+      if (c_ra.q_init_on) {                                   // distr_q.py:81-181 (lazy: same values, created on first touch)
+        unsigned rem = key - (unsigned)port * per_port;
+        int tgt = (int)(rem / 48u), semb = (int)((rem % 48u) / 3u);
+        int qi = c_m.qinit[port * c_L.NT + tgt];
+        if (qi >= 0 && semb != 0) row[1 + (qi & 15)] = (qi & 16) ? 1000.0 : 500.0;
       }
+      return row + 1;
     }
+    i++;
   }
-  g.sync();                                                              // the inserted row is visible to the whole group
-  return found;
+  e.h()->err |= SFL_ERR_Q_FULL;
+  return e.q() + 1;     // keep running on row 0 (flagged)
 }
 
 // integer sums: the accumulated step does not depend on the order in which the environments arrive
@@ -405,24 +379,22 @@ SFL_FN double td_value(double q, double lr, double reward, double gamma, double 
   return bootstrap ? dadd(dmul(one_m, q), dmul(lr, dadd(reward, dmul(gamma, mq)))) : dadd(dmul(one_m, q), dmul(lr, reward));
 }
 
-// distr_q.py:419-447 update (group-uniform; `on`: this group has an update to make)
-template <int G, class Env>
-SFL_NI void q_update(SFL_K, Env e, const Grp<G> &g, const Hp hp, const int on, unsigned key, int action, double reward,
+// distr_q.py:419-447 update
+template <class Env>
+SFL_NI void q_update(SFL_K, Env e, const Hp hp, unsigned key, int action, double reward,
                      const double *next_row, int prev_sw, int next_sw) {
-  double *row = q_find(K, e, g, hp, on, key);
-  if (!on) return;
+  double *row = q_row(K, e, hp, key);
   double lr = hp->lr;
   if (hp->lr_decay_rate != 1.0) lr = dmul(lr, lr_pow(hp->lr_decay_rate, e.sws()[prev_sw].ninter));
   const double q = row[action];
   double mq = 0.0;
   if (next_sw != prev_sw && next_row) {                          // distr_q.py:449-466 max_q ignores the mask; max_q(None) = 0
-    const int A = c_m.sw[next_sw].y;
+    int A = c_m.sw[next_sw].y;
     mq = next_row[0];
     SFL_NU
     for (int a = 1; a < A; a++) { const double v = next_row[a]; mq = v > mq ? v : mq; }
   }
   const double nq = td_value(q, lr, reward, hp->gamma, mq, next_sw != prev_sw);
-  if (g.gl != 0) return;
   if (Env::SQ) {                                                         // shared table: propose the TD step, leave the table alone
     const size_t i = (size_t)key * c_L.a_max + action;
     shared_add(c_ra.sq_d + i, c_ra.sq_c + i, (long long)llrint((nq - q) * 16777216.0));
@@ -519,160 +491,83 @@ SFL_FN void transition_semaphore(SFL_K, Env e, int source, int out_port, int tar
   }
 }
 
-// rail_network.py:303-416 with the four records it touches gathered up front (one round trip) and the rules applied to the
-// copies: out_port, target = its neighbour, unique = the forced-path port of target inside the next switch (or none) and
-// far = unique's neighbour.  They are four different ports unless the map loops a switch onto itself (unique == out_port or
-// unique == source): those decisions take the step-by-step version above.  `on`: group predicate; lane 0 stores.
-template <int G, class Env>
-SFL_FN void transition_train(SFL_K, Env e, const Grp<G> &g, const int on, int source, int out_port, int target, int h, int now, int st,
-                             int old_next, int old_prev) {
-  // (1) :315-323 -- release what the train holds on the switch it stands at and on the one it left: one port per lane
-  {
-    const int4 sa = c_m.sw[c_m.port[on ? old_next : 0].w];
-    const int4 sb = c_m.sw[c_m.port[(on && old_prev >= 0) ? old_prev : 0].w];
-    const int na = (on && st != ST_MALF) ? sa.x : 0, nb = (on && st != ST_MALF && old_prev >= 0) ? sb.x : 0;
-    SFL_UA
-    for (int base = 0; base < 8; base += G) {
-      const int j = base + g.gl;
-      if (j < 8) {
-        const int k = j & 3;
-        const int p = (j & 4) ? (k < nb ? sb.z + k : -1) : (k < na ? sa.z + k : -1);
-        if (p >= 0 && e.owner(p) == h) e.sem_drop(p);
-      }
-    }
-  }
-  g.sync();
-  const int unique = on ? c_m.port[target].z : -1;
-  const int slow = on && unique >= 0 && (unique == out_port || unique == source);
-  if (on && !slow) {
-    const int d_ot = c_m.port[out_port].y;
-    int4 up = make_int4(-1, 0, 0, 0);
-    if (unique >= 0) up = c_m.port[unique];
-    const int far_port = up.x;
-    const int4 none = make_int4(0, 0, -1, 0);
-    int4 r_out = e.sem()[out_port], r_tgt = e.sem()[target];
-    int4 r_unq = unique >= 0 ? e.sem()[unique] : none, r_far = unique >= 0 ? e.sem()[far_port] : none;
-    int w_out = 0, w_tgt = 0, w_unq = 0, w_far = 0;
-    if (r_out.z < 0) { r_out = make_int4(now, 3, h, SEM_OUT); w_out = 1; }                                   // :326-334
-    else if (r_out.w == SEM_OUT || r_out.x > now) { r_out = make_int4(now, 3, h, r_out.w); w_out = 1; }
-    if (r_tgt.z < 0) { r_tgt = make_int4(now, d_ot + 1, h, SEM_IN); w_tgt = 1; }                             // :336-344
-    else if (r_tgt.w == SEM_IN || r_tgt.x > now) { r_tgt = make_int4(now, d_ot + 1, h, r_tgt.w); w_tgt = 1; }
-    if (unique >= 0) {                                                                                       // :356 forced path
-      if (unique != target && (r_unq.z < 0 || r_unq.w == SEM_OUT || r_unq.x > now)) { r_unq = make_int4(now, d_ot + 1, h, SEM_OUT); w_unq = 1; }   // :368-378
-      if (r_unq.z < 0 || r_unq.x > now) { r_unq = make_int4(now, d_ot, h, SEM_OUT); w_unq = 1; }             // :380-388
-      if (far_port != source && far_port != out_port && far_port != unique &&                                // :390-402
-          (r_far.z < 0 || r_far.w == SEM_IN || r_far.x > now)) { r_far = make_int4(now, d_ot + up.y + 1, h, SEM_IN); w_far = 1; }
-    }
-    if (target != source && target != out_port &&                                                            // :404-414 moving edge
-        (r_tgt.z < 0 || r_tgt.w == SEM_OUT || r_tgt.x > now)) { r_tgt = make_int4(now, d_ot + 1, h, SEM_OUT); w_tgt = 1; }
-    if (g.gl == 0) {
-      if (w_out) e.sem_put(out_port, r_out);
-      if (w_tgt) e.sem_put(target, r_tgt);
-      if (w_unq) e.sem_put(unique, r_unq);
-      if (w_far) e.sem_put(far_port, r_far);
-    }
-  }
-  if (slow && g.gl == 0) transition_semaphore(K, e, source, out_port, target, h, now, ST_MALF, old_next, old_prev);   // (1) is done: skip it
-  g.sync();
-}
-
-// ------------------------------------------------------------------------------------------------ decision (group-uniform)
+// ------------------------------------------------------------------------------------------------ decision (first lane)
 template <class Env>
-SFL_FN int delay_at(SFL_K, Env e, int lane0, int tgt_index, int cell, int dir, int now, int la) {
+SFL_FN int delay_at(SFL_K, Env e, int tgt_index, int cell, int dir, int now, int la) {
   int d = c_m.dist[((size_t)tgt_index * (c_m.Hp * c_m.Wp) + cell) * 4 + dir];
-  if (d >= SFL_INF_DIST) { if (lane0) e.h()->err |= SFL_ERR_INF_DISTANCE; d = 0; }     // observer.py:35-36
+  if (d >= SFL_INF_DIST) { e.h()->err |= SFL_ERR_INF_DISTANCE; d = 0; }     // observer.py:35-36
   return now - la + d;                                                      // observer.py:41
 }
 
 // the tail of one iteration of distr_q.py:302-362 that must wait for the train ticks run inside env.step()
 // (switch_env.py:648-649): arrival flush (:345-356), interaction counter (:362), truncation (switch_env.py:652-657)
-template <int KIND, int G, class Env>
-SFL_FN void finish_decision(SFL_K, Env e, const Grp<G> &g, const Hp hp, int env_id, const int on) {
+template <int KIND, class Env>
+SFL_FN void finish_decision(SFL_K, Env e, const Hp hp, int env_id) {
   const bool TRACE = KIND == K_FULL;
   const int mode = run_mode<KIND>(K);
   EnvHdr *h = e.h();
-  const int lane0 = g.gl == 0;
-  const int learning = mode == SFL_MODE_LEARN || mode == SFL_MODE_REPLAY;
-  unsigned long long fresh = (on && learning) ? (h->done_mask & ~h->at_dest_mask) : 0ull;
-  if (g.wany(fresh != 0ull)) {
-    const unsigned long long all_fresh = fresh;
+  if (mode == SFL_MODE_LEARN || mode == SFL_MODE_REPLAY) {
+    unsigned long long fresh = h->done_mask & ~h->at_dest_mask;
     SFL_NU
-    while (g.wany(fresh != 0ull)) {
-      const int have = fresh != 0ull;
-      const int t = have ? ffs64(fresh) : 0;
-      fresh &= fresh - 1;
-      const int4 b = e.trb()[t];
-      const int n = have ? (b.y >> 16) & 0xFF : 0;
+    while (fresh) {
+      int t = ffs64(fresh); fresh &= fresh - 1;
+      h->at_dest_mask |= 1ull << t;
+      int4 b = e.trb()[t];
+      int n = (b.y >> 16) & 0xFF;
       SFL_NU
-      for (int i = 0; g.wany(i < n); i++) {
-        int2 pe = make_int2(0, 0);
-        if (i < n) pe = e.pend()[t * c_L.pend_cap + i];
-        q_update(K, e, g, hp, i < n, (unsigned)pe.x, (pe.y >> 24) & 15, 1000.0, nullptr, (pe.y >> 12) & 0xFFF, -1);
+      for (int i = 0; i < n; i++) {
+        int2 pe = e.pend()[t * c_L.pend_cap + i];
+        q_update(K, e, hp, (unsigned)pe.x, (pe.y >> 24) & 15, 1000.0, nullptr, (pe.y >> 12) & 0xFFF, -1);
       }
-      if (have && lane0) e.trb()[t].y = b.y & 0xFFFF;
+      b.y &= 0xFFFF;
+      e.trb()[t] = b;
     }
-    if (all_fresh && lane0) h->at_dest_mask |= all_fresh;
+    SwS *ss = e.sws() + h->pending_fin;
+    ss->ninter++;
+    ss->eps_pow = dmul(ss->eps_pow, hp->epsilon_decay_rate);
   }
-  if (on && lane0) {
-    if (learning) {
-      SwS *ss = e.sws() + h->pending_fin;
-      ss->ninter++;
-      ss->eps_pow = dmul(ss->eps_pow, hp->epsilon_decay_rate);
-    }
-    h->pending_fin = -1;
-    if (h->step_counter > c_ra.max_steps) h->truncated = 1;
-    if (TRACE) {
-      if (c_ra.trace_dec && h->cur_dec >= 0 && h->cur_dec < c_ra.dec_cap) {
-        sfl_dec_rec *rec = c_ra.trace_dec + (size_t)env_id * c_ra.dec_cap + h->cur_dec;
-        rec->arrived = h->done_mask;
-        rec->done = h->terminated | (h->truncated << 1);
-        if (c_ra.trace_sem_buf) {
-          int4 *dst = c_ra.trace_sem_buf + ((size_t)env_id * c_ra.dec_cap + h->cur_dec) * c_L.NP;
-          SFL_NU
-          for (int p = 0; p < c_L.NP; p++) { int4 r = e.sem()[p]; r.y += r.x; dst[p] = r; }      // traced as {t0, t1, train, type}
-        }
+  h->pending_fin = -1;
+  if (h->step_counter > c_ra.max_steps) h->truncated = 1;
+  if (TRACE) {
+    if (c_ra.trace_dec && h->cur_dec >= 0 && h->cur_dec < c_ra.dec_cap) {
+      sfl_dec_rec *rec = c_ra.trace_dec + (size_t)env_id * c_ra.dec_cap + h->cur_dec;
+      rec->arrived = h->done_mask;
+      rec->done = h->terminated | (h->truncated << 1);
+      if (c_ra.trace_sem_buf) {
+        int4 *dst = c_ra.trace_sem_buf + ((size_t)env_id * c_ra.dec_cap + h->cur_dec) * c_L.NP;
+        SFL_NU
+        for (int p = 0; p < c_L.NP; p++) { int4 r = e.sem()[p]; r.y += r.x; dst[p] = r; }      // traced as {t0, t1, train, type}
       }
-      h->cur_dec = -1;
     }
+    h->cur_dec = -1;
   }
-  g.sync();
 }
 
-// observation of train t at its active switch (observer.py:246-308 + switch_agents.py:104-134); group-uniform result
+// observation of train t at its active switch (observer.py:246-308 + switch_agents.py:104-134)
 struct Obs { int s, P, A, p0, a0, cur, semb, mask, ok; unsigned key; };
-template <int G, class Env>
-SFL_FN Obs observe(SFL_K, Env e, const Grp<G> &g, const int on, int t, int now, const int4 ta, const int4 tb) {
+template <class Env>
+SFL_FN Obs observe(SFL_K, Env e, int t, int now, const int4 ta, const int4 tb) {
   Obs ob;
-  ob.s = on ? (tb.y & 0xFFFF) : 0;
+  ob.s = tb.y & 0xFFFF;
   const int4 sw = c_m.sw[ob.s];
   ob.P = sw.x; ob.A = sw.y; ob.p0 = sw.z; ob.a0 = sw.w;
   const int4 tr0 = c_m.train0[t], tr1 = c_m.train1[t];
   const int my_port = (int)((unsigned)ta.w >> 16);
+  // compute_delay's distance lookup goes out before the port checks: its latency overlaps with theirs
+  const int dist_now = c_m.dist[((size_t)tr0.w * (c_m.Hp * c_m.Wp) + ta.x) * 4 + (ta.y & 0xFF)];
+  int semb = 0;
+  SFL_NU
+  for (int k = 0; k < ob.P; k++)
+    if (!port_blocked(e, c_m.port[ob.p0 + k].x, ob.p0 + k, t, now)) semb |= 1 << k;
+  ob.semb = semb;
   ob.cur = my_port - ob.p0;
-  ob.ok = on && ob.cur >= 0 && ob.cur < ob.P;
-  // the distance lookup of compute_delay goes out first, the semaphore records of the ports right behind it
-  int dist = 0;
-  if (ob.ok) dist = c_m.dist[((size_t)tr0.w * (c_m.Hp * c_m.Wp) + ta.x) * 4 + (ta.y & 0xFF)];
-  // check_port_blocked per port (observer.py:269-278): item j = port (j & 3), j < 4 the rule on the neighbour ("next") port,
-  // j >= 4 the rule on the port itself -- one item per lane, the verdicts meet in a vote
-  unsigned bits = 0;
-  SFL_UA
-  for (int base = 0; base < 8; base += G) {
-    const int j = base + g.gl;
-    int b = 0;
-    if (on && j < 8 && (j & 3) < ob.P) {
-      const int port = ob.p0 + (j & 3);
-      b = (j & 4) ? rule_port(e, port, t, now, SEM_IN) : rule_port(e, c_m.port[port].x, t, now, SEM_OUT);
-    }
-    bits |= (g.ballot(b) & 0xFFu) << base;
-  }
-  ob.semb = (int)(~(bits | (bits >> 4)) & ((1u << ob.P) - 1u));
+  ob.ok = ob.cur >= 0 && ob.cur < ob.P;
   ob.key = 0u; ob.mask = 0;
   if (!ob.ok) return ob;
-  if (dist >= SFL_INF_DIST) { if (g.gl == 0) e.h()->err |= SFL_ERR_INF_DISTANCE; dist = 0; }     // observer.py:35-36
-  const int delay = now - tr1.y + dist;                                           // observer.py:41
-  const int level = delay <= 0 ? 0 : (delay <= (tr1.y - tr1.x) * 20 ? 1 : 2);     // observer.py:239-244
-  ob.key = (((unsigned)(ob.p0 + ob.cur) * c_L.NT + tr0.w) * 16u + ob.semb) * 3u + level;
+  int delay = now - tr1.y + dist_now;                                             // observer.py:41
+  if (dist_now >= SFL_INF_DIST) { e.h()->err |= SFL_ERR_INF_DISTANCE; delay = now - tr1.y; }     // observer.py:35-36
+  int level = delay <= 0 ? 0 : (delay <= (tr1.y - tr1.x) * 20 ? 1 : 2);           // observer.py:239-244
+  ob.key = (((unsigned)(ob.p0 + ob.cur) * c_L.NT + tr0.w) * 16u + semb) * 3u + level;
   const int4 px = c_m.pexit[ob.p0 + ob.cur];                                      // switch_agents.py:104-134
   int mask = 1 << (ob.A - 1);
   {
@@ -680,71 +575,61 @@ SFL_FN Obs observe(SFL_K, Env e, const Grp<G> &g, const int on, int t, int now, 
 #if SFL_DEV
 #pragma unroll
 #endif
-    for (int i = 0; i < 3; i++) if (i < px.x && ((ob.semb >> ((ex[i] >> 4) & 3)) & 1)) mask |= 1 << (ex[i] & 15);
+    for (int i = 0; i < 3; i++) if (i < px.x && ((semb >> ((ex[i] >> 4) & 3)) & 1)) mask |= 1 << (ex[i] & 15);
   }
   ob.mask = mask;
   return ob;
 }
 
 // one switch-agent decision: observe (O1-O3) -> act (Q1) -> apply (E2, E3, R1) -> Q-update (Q2, Q3)
-template <int KIND, int G, class Env>
-SFL_FN void decide(SFL_K, Env e, const Grp<G> &g, const Hp hp, int env_id, const int has, int t) {
+template <int KIND, class Env>
+SFL_FN void decide(SFL_K, Env e, const Hp hp, int env_id, int t) {
   const bool TRACE = KIND == K_FULL;
   const int mode = run_mode<KIND>(K);
   EnvHdr *h = e.h();
-  const int lane0 = g.gl == 0;
   const int now = h->elapsed;
   int4 ta = e.tra()[t], tb = e.trb()[t];
+  // What does not depend on the observation is loaded before it, so that these round trips to HBM overlap with the port
+  // checks instead of following them one by one: last()'s reward, epsilon's decay product, the head of the pending list
   const int learning = mode == SFL_MODE_LEARN || mode == SFL_MODE_REPLAY;
-  // loads whose address does not depend on the observation go out before it: last()'s reward, epsilon's decay product
-  const int s0 = has ? (tb.y & 0xFFFF) : 0;
-  int reward_in = 0;
+  const int s_early = tb.y & 0xFFFF;
+  const int reward_in = e.rewards()[s_early * c_L.T + t];                         // last(): _cumulative_rewards[agent][train]
   double eps_pow = 1.0;
-  if (has) {
-    reward_in = e.rewards()[s0 * c_L.T + t];                                      // last(): _cumulative_rewards[agent][train]
-    if (mode == SFL_MODE_LEARN) eps_pow = e.sws()[s0].eps_pow;
-  }
-  const Obs ob = observe(K, e, g, has, t, now, ta, tb);
-  if (has && !ob.ok && lane0) {
+  if (mode == SFL_MODE_LEARN) eps_pow = e.sws()[s_early].eps_pow;
+  int2 pend0 = make_int2(0, -1);
+  if (learning && ((tb.y >> 16) & 0xFF)) pend0 = e.pend()[t * c_L.pend_cap];
+  const Obs ob = observe(K, e, t, now, ta, tb);
+  if (!ob.ok) {
     // observer.py:294-307: "No train detected at active switch" -- the reference then dies on an unbound current_port
     // (:307).  There is nothing to be faithful to past this point: flag the env, abandon the episode, carry on.
     h->err |= SFL_ERR_NO_TRAIN_AT_SWITCH; h->aborted++; h->truncated = 1;
+    return;
   }
-  const int on = has && ob.ok;
   const int s = ob.s, A = ob.A, p0 = ob.p0, a0 = ob.a0, cur = ob.cur, mask = ob.mask;
   const unsigned key = ob.key;
   const int4 tr0 = c_m.train0[t], tr1 = c_m.train1[t];
   const int pos = ta.x, dir = ta.y & 0xFF, st = (ta.y >> 8) & 0xFF;
   const int my_port = (int)((unsigned)ta.w >> 16);
-  // the pending updates of this train (update_dict, distr_q.py:283): one entry per lane, the switch match is a vote
-  const int n_pend = (on && learning) ? (tb.y >> 16) & 0xFF : 0;
-  unsigned hit_bits = 0;
-  SFL_NU
-  for (int base = 0; base < c_L.pend_cap; base += G) {
-    const int i = base + g.gl;
-    int m = 0;
-    if (i < n_pend) m = (e.pend()[t * c_L.pend_cap + i].y & 0xFFF) == s;
-    hit_bits |= g.ballot(m) << base;
-  }
-  const int hit = hit_bits ? ffs64(hit_bits) : -1;
-  int2 pe_hit = make_int2(0, 0);
-  if (hit >= 0) pe_hit = e.pend()[t * c_L.pend_cap + hit];
-  const int prev_sw_hit = (pe_hit.y >> 12) & 0xFFF;
   // ---- act (distr_q.py:312-320 / :211)
-  int action = -1, exploited = 0, err = 0;
-  if (on && (mode == SFL_MODE_REPLAY || mode == SFL_MODE_STEP)) {
-    const int cursor = mode == SFL_MODE_STEP ? 0 : h->act_cursor;     // STEP: the host's action for this decision
-    if (cursor >= c_ra.act_cap) { err |= SFL_ERR_REPLAY_UNDERRUN; action = A - 1; }
+  double *my_row = nullptr;
+  int action = -1;
+  if (mode == SFL_MODE_REPLAY || mode == SFL_MODE_STEP) {
+    if (mode == SFL_MODE_STEP) h->act_cursor = 0;              // the host's action for this decision
+    int exploited = 0;
+    if (h->act_cursor >= c_ra.act_cap) { h->err |= SFL_ERR_REPLAY_UNDERRUN; action = A - 1; }
     else {
-      action = c_ra.replay_act[(size_t)env_id * c_ra.act_cap + cursor];
+      action = c_ra.replay_act[(size_t)env_id * c_ra.act_cap + h->act_cursor++];
       // bit 6 of a recorded action: the learner exploited, i.e. max_action was consulted -- which inserts the row
       // (distr_q.py:318-319, 482); the replay then also checks that the recorded action IS the argmax
       if (mode == SFL_MODE_REPLAY && action >= 0 && (action & 0x40)) { exploited = 1; action &= 0x3F; }
-      if (lane0) h->act_cursor = cursor + 1;
     }
-    if (action < 0 || action >= A) { err |= SFL_ERR_BAD_ACTION; action = A - 1; }
-  } else if (on && mode == SFL_MODE_LEARN) {
-    const double eps = dmul(hp->epsilon, eps_pow);
+    if (action < 0 || action >= A) { h->err |= SFL_ERR_BAD_ACTION; action = A - 1; }
+    if (exploited) {
+      my_row = q_row(K, e, hp, key);
+      if (max_action(my_row, A, mask) != action) h->err |= SFL_ERR_REPLAY_DIVERGED;
+    }
+  } else if (mode == SFL_MODE_LEARN) {
+    double eps = dmul(hp->epsilon, eps_pow);
     // one Philox4x32-10 block per PAIR of decisions: counter (step_counter >> 1, episode, 0x5F1, 0), key = env seed; the
     // even decision of the pair uses words 0-1, the odd one words 2-3 (kept in the header, so the stream does not depend
     // on how the run is cut into launches)
@@ -753,10 +638,10 @@ SFL_FN void decide(SFL_K, Env e, const Grp<G> &g, const Hp hp, int env_id, const
     if ((h->step_counter & 1) && h->eps_tag == pair) { ux = h->eps_z; uy = h->eps_w; }
     else {
       const U4 u = philox4x32((unsigned)pair, (unsigned)(hp->episode_base + h->episode), 0x5F1u, 0u, (unsigned)hp->seed, (unsigned)(hp->seed >> 32));
+      h->eps_tag = pair; h->eps_z = u.z; h->eps_w = u.w;
       if (h->step_counter & 1) { ux = u.z; uy = u.w; } else { ux = u.x; uy = u.y; }
-      if (lane0) { h->eps_tag = pair; h->eps_z = u.z; h->eps_w = u.w; }
     }
-    const double u01 = ((double)ux + 0.5) * (1.0 / 4294967296.0);
+    double u01 = ((double)ux + 0.5) * (1.0 / 4294967296.0);
     if (u01 < eps) {                                       // explore: uniform over the allowed actions
       int pick = (int)(((unsigned long long)uy * (unsigned)popc32((unsigned)mask)) >> 32);
       unsigned mm = (unsigned)mask;
@@ -765,28 +650,22 @@ SFL_FN void decide(SFL_K, Env e, const Grp<G> &g, const Hp hp, int env_id, const
       action = ffs64(mm);
     }
   }
-  // the row of this state is needed to exploit (distr_q.py:318-319, test() :211) and as the successor row of a pending
-  // update that bootstraps (max_q creates it, :463-465 -- but only when consulted: not for a train that stayed, :444-447)
-  const int exploit = on && (action < 0 || exploited);
-  const int need_row = exploit || (hit >= 0 && prev_sw_hit != s);
-  double *my_row = q_find(K, e, g, hp, need_row, key);
-  if (exploit) {
-    const int best = max_action(my_row, A, mask);
-    if (exploited) { if (best != action) err |= SFL_ERR_REPLAY_DIVERGED; }
-    else action = best;
+  if (action < 0) {                                        // exploit (distr_q.py:318-319) / test() (:211)
+    my_row = q_row(K, e, hp, key);
+    action = max_action(my_row, A, mask);
   }
-  if (!on) action = 0;
   // ---- apply (switch_env.py:203-294, switch_agents.py:136-168)
   int moving = 0, move2 = A_STOP, in_port = my_port, out_port = my_port;
-  if (on && action != A - 1) {
-    const int4 ac = c_m.act[a0 + action];
+  if (action != A - 1) {
+    int4 ac = c_m.act[a0 + action];
     if (ac.x == cur) { moving = 1; move2 = ac.z; in_port = p0 + ac.x; out_port = p0 + ac.y; }
   }
   int next_switch = s, next_port = -1;
-  if (moving) next_port = c_m.port[out_port].x;                                     // rail_network.py:246-278
-  const int old_prev = (tb.x & 0xFFFF) == 0xFFFF ? -1 : (tb.x & 0xFFFF);
-  if (g.wany(moving)) transition_train(K, e, g, moving, in_port, out_port, moving ? next_port : 0, t, now, st, my_port, old_prev);
-  if (moving) {
+  if (moving) {                                                                   // rail_network.py:246-278
+    int4 op = c_m.port[out_port];
+    next_port = op.x;
+    int old_prev = (tb.x & 0xFFFF) == 0xFFFF ? -1 : (tb.x & 0xFFFF);
+    transition_semaphore(K, e, in_port, out_port, next_port, t, now, st, my_port, old_prev);
     tb.x = (out_port & 0xFFFF) | (in_port << 16);                                 // prev_port = out, source_port = in
     ta.w = (ta.w & 0xFFFF) | (next_port << 16);
     next_switch = c_m.port[next_port].w;
@@ -795,86 +674,79 @@ SFL_FN void decide(SFL_K, Env e, const Grp<G> &g, const Hp hp, int env_id, const
   int pl = ta.z >> 16;
   if (moving && pl > 0) { plan = (plan & 0xFu) | ((unsigned)move2 << 4); pl = 2; }            // :257-266
   else if (!moving) {                                                             // :267-270
-    if (pl >= SFL_PLAN_CAP) { if (on) err |= SFL_ERR_PLAN_FULL; pl = SFL_PLAN_CAP - 1; }
+    if (pl >= SFL_PLAN_CAP) { h->err |= SFL_ERR_PLAN_FULL; pl = SFL_PLAN_CAP - 1; }
     plan = ((plan << 4) | A_STOP) & 0xFFFFu; pl++;
   } else { plan = A_FWD | ((unsigned)move2 << 4); pl = 2; }                       // :271-272
   ta.z = (int)plan | (pl << 16);
+  e.tra()[t] = ta;
   int all_blocked = 1;                                                            // :274-282
-  if (on && (plan & 0xFu) == A_STOP) {                   // only consulted for the stop penalty (reward_func.py:61-76)
+  if ((plan & 0xFu) == A_STOP) {                         // only consulted for the stop penalty (reward_func.py:61-76)
     if (moving) all_blocked = port_blocked(e, next_port, out_port, t, now);
     else all_blocked = (mask == (1 << (A - 1)));         // no transition happened: the observe bits still hold
   }
   int cell = pos, d2 = dir;                                                       // reward_func.py:23-78
-  if (on) {
+  {
     unsigned pp = plan;
     SFL_NU
     for (int i = 0; i < pl; i++, pp >>= 4) {
-      const int a = pp & 0xF;
-      if (a != A_STOP) { const Mv c = check_action(K, a, cell, d2); cell = c.cell; d2 = c.dir; }
+      int a = pp & 0xF;
+      if (a != A_STOP) { Mv c = check_action(K, a, cell, d2); cell = c.cell; d2 = c.dir; }
     }
   }
-  int curr = 0;
-  if (on) curr = delay_at(K, e, lane0, tr0.w, cell, d2, now, tr1.y);
+  int curr = delay_at(K, e, tr0.w, cell, d2, now, tr1.y);
   int reward_out = tb.z - curr;
   if (!all_blocked && (plan & 0xFu) == A_STOP) reward_out -= 1300;
+  e.rewards()[next_switch * c_L.T + t] = reward_out;                              // switch_env.py:289
   tb.z = curr;                                                                    // switch_env.py:291
+  h->step_counter++;
   // ---- learn (distr_q.py:329-342)
-  if (g.wany(hit >= 0))
-    q_update(K, e, g, hp, hit >= 0, (unsigned)pe_hit.x, (pe_hit.y >> 24) & 15, (double)reward_in, my_row, prev_sw_hit, s);
-  // update_dict[(next_switch, train)] = (obs, action, agent): the same key overwrites in place (:340-342); the consumed
-  // entry leaves the list first
-  unsigned same_bits = 0;
-  SFL_NU
-  for (int base = 0; base < c_L.pend_cap; base += G) {
-    const int i = base + g.gl;
-    int m = 0;
-    if (i < n_pend && i != hit) m = (e.pend()[t * c_L.pend_cap + i].y & 0xFFF) == next_switch;
-    same_bits |= g.ballot(m) << base;
-  }
-  if (on && learning) {
-    int n = n_pend - (hit >= 0 ? 1 : 0);
-    int same = -1;                                                                // last match, as an index into the list after the removal
-    if (same_bits) { same = 31 - clz32(same_bits); if (hit >= 0 && same > hit) same--; }
-    const int append = same < 0 && n < c_L.pend_cap;
-    if (same < 0 && !append) err |= SFL_ERR_PEND_FULL;
-    if (lane0) {
-      int2 *pend = e.pend() + t * c_L.pend_cap;
-      if (hit >= 0) {
-        SFL_NU
-        for (int j = hit; j < n; j++) pend[j] = pend[j + 1];
-      }
-      const int meta = next_switch | (s << 12) | (action << 24);
-      if (same >= 0) pend[same] = make_int2((int)key, meta);
-      else if (append) pend[n] = make_int2((int)key, meta);
+  if (learning) {
+    int n = (tb.y >> 16) & 0xFF;
+    int2 *pend = e.pend() + t * c_L.pend_cap;
+    int hit = -1, same = -1;
+    SFL_NU
+    for (int i = 0; i < n; i++) {
+      int nsw = (i ? pend[i].y : pend0.y) & 0xFFF;
+      if (nsw == s && hit < 0) hit = i;
     }
-    if (append) n++;
+    if (hit >= 0) {
+      int2 pe = hit ? pend[hit] : pend0;
+      const int prev_sw = (pe.y >> 12) & 0xFFF;
+      // max_q creates the successor row (distr_q.py:463-465) -- but only when it is consulted: not for a train that
+      // stayed at the same switch (:444-447)
+      if (prev_sw != s && !my_row) my_row = q_row(K, e, hp, key);
+      q_update(K, e, hp, (unsigned)pe.x, (pe.y >> 24) & 15, (double)reward_in, my_row, prev_sw, s);
+      SFL_NU
+      for (int j = hit; j + 1 < n; j++) pend[j] = pend[j + 1];
+      n--;
+    }
+    // update_dict[(next_switch, train)] = (obs, action, agent): the same key overwrites in place (:340-342)
+    int meta = next_switch | (s << 12) | (action << 24);
+    SFL_NU
+    for (int i = 0; i < n; i++) if ((pend[i].y & 0xFFF) == next_switch) same = i;
+    if (same >= 0) pend[same] = make_int2((int)key, meta);
+    else if (n >= c_L.pend_cap) h->err |= SFL_ERR_PEND_FULL;
+    else { pend[n] = make_int2((int)key, meta); n++; }
     tb.y = (tb.y & 0xFFFF) | (n << 16);
   }
-  if (on && lane0) {
-    e.tra()[t] = ta;
-    e.trb()[t] = tb;
-    e.rewards()[next_switch * c_L.T + t] = reward_out;                            // switch_env.py:289
-    h->step_counter++;
-    h->cum_reward += (double)reward_in;                                           // distr_q.py:360
-    if (TRACE) {
-      if (c_ra.trace_dec) {
-        h->cur_dec = h->n_dec_logged;
-        if (h->n_dec_logged < c_ra.dec_cap) {
-          sfl_dec_rec *rec = c_ra.trace_dec + (size_t)env_id * c_ra.dec_cap + h->n_dec_logged;
-          rec->ep = h->episode; rec->tick = now; rec->sw = s; rec->train = t; rec->key = key; rec->mask = mask;
-          rec->action = action; rec->next_sw = next_switch; rec->reward = reward_in; rec->done = 0; rec->arrived = 0;
-        }
-        h->n_dec_logged++;
+  e.trb()[t] = tb;
+  h->cum_reward += (double)reward_in;                                             // distr_q.py:360
+  if (TRACE) {
+    if (c_ra.trace_dec) {
+      h->cur_dec = h->n_dec_logged;
+      if (h->n_dec_logged < c_ra.dec_cap) {
+        sfl_dec_rec *rec = c_ra.trace_dec + (size_t)env_id * c_ra.dec_cap + h->n_dec_logged;
+        rec->ep = h->episode; rec->tick = now; rec->sw = s; rec->train = t; rec->key = key; rec->mask = mask;
+        rec->action = action; rec->next_sw = next_switch; rec->reward = reward_in; rec->done = 0; rec->arrived = 0;
       }
-      h->last_next_sw = next_switch;
+      h->n_dec_logged++;
     }
-    h->decisions++;
-    if (mask == (1 << (A - 1))) h->forced_stops++;
-    if (action == A - 1) h->stop_actions++;
-    h->pending_fin = s;
   }
-  if (err && lane0) h->err |= err;
-  g.sync();
+  if (TRACE) h->last_next_sw = next_switch;
+  h->decisions++;
+  if (mask == (1 << (A - 1))) h->forced_stops++;
+  if (action == A - 1) h->stop_actions++;
+  h->pending_fin = s;
 }
 
 // ------------------------------------------------------------------------------------------------ reset (E1)
@@ -1230,29 +1102,24 @@ SFL_NI void episode_end(SFL_K, Env e, int env_id) {   // first lane
 // ------------------------------------------------------------------------------------------------ SFL_MODE_STEP
 // The AEC protocol driven from the host (switch_env.py:616-666): report the waiting decision the way AECEnv.last()
 // would, or the end of the episode.  First lane of the group.
-template <int G, class Env>
-SFL_FN void step_report(SFL_K, Env e, const Grp<G> &g, int env_id, const int on, int t) {
+template <class Env>
+SFL_FN void step_report(SFL_K, Env e, int env_id, int t) {
   EnvHdr *h = e.h();
-  const int has = on && t >= 0;
-  const int tt = has ? t : 0;
-  const int4 ta = e.tra()[tt], tb = e.trb()[tt];
-  const Obs ob = observe(K, e, g, has, tt, h->elapsed, ta, tb);
-  if (on && g.gl == 0) {
-    sfl_step_rec *o = c_ra.step_out + env_id;
-    o->pending = 0; o->sw = -1; o->train = -1; o->key = 0u; o->mask = 0;
-    if (has) {
-      if (!ob.ok) { h->err |= SFL_ERR_NO_TRAIN_AT_SWITCH; h->aborted++; h->truncated = 1; }    // last() raises in the reference
-      else {
-        o->pending = 1; o->sw = ob.s; o->train = t; o->key = ob.key; o->mask = ob.mask;
-        SFL_NU
-        for (int k = 0; k < c_L.T; k++) o->rewards[k] = e.rewards()[ob.s * c_L.T + k];
-        h->cur_train = t;
-      }
+  sfl_step_rec *o = c_ra.step_out + env_id;
+  o->pending = 0; o->sw = -1; o->train = -1; o->key = 0u; o->mask = 0;
+  if (t >= 0) {
+    const int4 ta = e.tra()[t], tb = e.trb()[t];
+    const Obs ob = observe(K, e, t, h->elapsed, ta, tb);
+    if (!ob.ok) { h->err |= SFL_ERR_NO_TRAIN_AT_SWITCH; h->aborted++; h->truncated = 1; }    // last() raises in the reference
+    else {
+      o->pending = 1; o->sw = ob.s; o->train = t; o->key = ob.key; o->mask = ob.mask;
+      SFL_NU
+      for (int k = 0; k < c_L.T; k++) o->rewards[k] = e.rewards()[ob.s * c_L.T + k];
+      h->cur_train = t;
     }
-    o->done = h->terminated | (h->truncated << 1);
-    o->elapsed = h->elapsed; o->last_next_sw = h->last_next_sw; o->arrived = h->done_mask;
   }
-  g.sync();
+  o->done = h->terminated | (h->truncated << 1);
+  o->elapsed = h->elapsed; o->last_next_sw = h->last_next_sw; o->arrived = h->done_mask;
 }
 
 template <int G, int KIND, bool TH, bool SQ, bool ONE>
@@ -1308,12 +1175,12 @@ SFL_FN void env_run(SFL_K, int env_id, unsigned stage, char *host_scratch) {
   }
   const int stepping = TRACE && run_mode<KIND>(K) == SFL_MODE_STEP;
   int paused = 0;                                                         // stepping: a decision waits for the host
-  if (stepping) {                                                         // apply the action the host chose for the waiting decision
-    const int on = live && h->cur_train >= 0;
-    const int t = on ? h->cur_train : 0;
+  if (stepping) {
+    if (live && g.gl == 0) {
+      if (h->cur_train >= 0) { decide<KIND>(K, e, hp, env_id, h->cur_train); h->cur_train = -1; }
+      else h->last_next_sw = -1;
+    }
     g.sync();
-    if (live && g.gl == 0) { if (on) h->cur_train = -1; else h->last_next_sw = -1; }
-    decide<KIND>(K, e, g, hp, env_id, on, t);
     if (live) R.ended = h->terminated | h->truncated;
   }
   int any_reset = g.wany(live && need_reset);                             // warp-uniform; can only change in a decision phase
@@ -1323,28 +1190,23 @@ SFL_FN void env_run(SFL_K, int env_id, unsigned stage, char *host_scratch) {
     const unsigned wf = g.wor((live && !paused ? 1u : 0u) | (due ? 2u : 0u));   // one warp-wide OR: anybody running / due
     if (!(wf & 1u)) break;
     if (wf & 2u) {
-      if (stepping) {
-        const int fin = due && h->pending_fin >= 0 && (h->active_mask || h->terminated);
-        if (g.wany(fin)) finish_decision<KIND>(K, e, g, hp, env_id, fin);
+      if (due && g.gl == 0 && stepping) {
+        if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<KIND>(K, e, hp, env_id);
         int t = -1;
-        if (due && !(h->terminated || h->truncated) && h->active_mask) t = ffs64(h->active_mask);
-        g.sync();
-        if (t >= 0 && g.gl == 0) h->active_mask &= h->active_mask - 1;
-        step_report(K, e, g, env_id, due, t);
-      } else {
-        int more = due;
+        if (!(h->terminated || h->truncated) && h->active_mask) { t = ffs64(h->active_mask); h->active_mask &= h->active_mask - 1; }
+        step_report(K, e, env_id, t);
+        if (h->terminated || h->truncated) episode_end(K, e, env_id);
+      } else if (due && g.gl == 0) {
         SFL_NU
-        while (g.wany(more)) {                                            // agent_iter: FIFO in train-handle order
-          const int fin = more && h->pending_fin >= 0 && (h->active_mask || h->terminated);
-          if (g.wany(fin)) finish_decision<KIND>(K, e, g, hp, env_id, fin);
-          int t = 0;
-          if (more) { if (h->terminated || h->truncated || !h->active_mask) more = 0; else t = ffs64(h->active_mask); }
-          g.sync();
-          if (more && g.gl == 0) h->active_mask &= h->active_mask - 1;
-          if (g.wany(more)) decide<KIND>(K, e, g, hp, env_id, more, t);
+        for (;;) {                                                        // agent_iter: FIFO in train-handle order
+          if (h->pending_fin >= 0 && (h->active_mask || h->terminated)) finish_decision<KIND>(K, e, hp, env_id);
+          if (h->terminated || h->truncated || !h->active_mask) break;
+          int t = ffs64(h->active_mask);
+          h->active_mask &= h->active_mask - 1;
+          decide<KIND>(K, e, hp, env_id, t);
         }
+        if (h->terminated || h->truncated) episode_end(K, e, env_id);
       }
-      if (due && g.gl == 0 && (h->terminated || h->truncated)) episode_end(K, e, env_id);
       g.sync();
       if (due) { need_reset = h->need_reset; R.active = 0; if (stepping) paused = h->cur_train >= 0; }
       any_reset = g.wany(live && need_reset);
