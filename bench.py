@@ -247,6 +247,13 @@ class Ctx:
         return [float(x) for x in t.tolist()], [int(x) for x in c.tolist()]
 
 
+def engine_kwargs(parts: int) -> dict:
+    """Scheduling knobs bench.py passes to every Engine of a workload with ``parts`` maps: with several maps in flight at
+    once the GPU is full, so the large-map kernel built for 7 CTAs per SM beats the 4-CTA ("roomy") build the library would
+    pick for one such launch alone (C3: 4.41e8 against 4.03e8 decisions/s)."""
+    return {"roomy": False} if parts > 1 else {}
+
+
 def kernel_counters(workload):
     """Per-launch ncu counters of the workload's k_run (committed under profiles/, NOT measured by this run)."""
     path = os.path.join(ROOT, "profiles", "kernel_counters.json")
@@ -269,7 +276,11 @@ def run_block(cx: Ctx, wl: str, args, steps: int, warmup: int, sampler=None, flu
     parts = len(fxs)
     Bp = B // parts                                                       # environments per map
     B = Bp * parts
-    kw = {"lanes": args.lanes or None, "cta_warps": args.cta_warps or None} if head else {}
+    kw = engine_kwargs(parts)
+    if head:
+        kw.update({"lanes": args.lanes or None, "cta_warps": args.cta_warps or None})
+        if args.roomy >= 0:
+            kw["roomy"] = bool(args.roomy)
 
     def seeds_of(k):
         return np.arange(Bp, dtype=np.uint64) + np.uint64(SEED + cx.rank * B + k * Bp)
@@ -283,17 +294,33 @@ def run_block(cx: Ctx, wl: str, args, steps: int, warmup: int, sampler=None, flu
         if shared:
             eng.init_shared_q(HP["default_q"])
     sync_ev = []
+    # Several maps (C3): one stream per engine, so that the launches of a step run concurrently -- a launch carries its map
+    # as a kernel parameter, nothing is shared between contexts.  The step is bracketed on the current stream.
+    streams = [torch.cuda.Stream(device=cx.dev) for _ in engs] if parts > 1 else None
+
+    def launch_all(timed=False):
+        if streams is None:
+            for eng in engs:
+                launch(eng, timed)
+            return
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for eng, st in zip(engs, streams):
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                launch(eng, timed)
+            join = torch.cuda.Event()
+            join.record(st)
+            cur.wait_event(join)
 
     def launch(eng, timed=False):
-        eng.run(backend.MODE_LEARN, ticks)
         if shared:
-            if timed:
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-            eng.shared_q_sync(cx.dist)                                    # all-reduce of the accumulators + apply kernel
-            if timed:
-                b.record()
-                sync_ev.append((a, b))
+            # overlapped schedule: the integer all-reduce (NCCL) + apply of this step run on a second stream while the
+            # next launch already reads the other table (Engine.run_shared)
+            eng.run_shared(ticks, cx.dist)
+        else:
+            eng.run(backend.MODE_LEARN, ticks)
 
     # Timing hygiene: the env state + Q tables are larger than L2, but on the small map the lines a launch actually touches
     # are not (ncu: 11 MB of DRAM traffic per launch), so L2 is flushed between the timed steps (256 MB written); the
@@ -303,8 +330,7 @@ def run_block(cx: Ctx, wl: str, args, steps: int, warmup: int, sampler=None, flu
     if flush_l2 == "on" or (flush_l2 == "auto" and state_bytes < (1 << 30)):
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=cx.dev)
     for _ in range(warmup):
-        for eng in engs:
-            launch(eng)
+        launch_all()
     cx.barrier()
 
     def totals():
@@ -325,17 +351,29 @@ def run_block(cx: Ctx, wl: str, args, steps: int, warmup: int, sampler=None, flu
         if flush is not None:
             flush.zero_()
         a.record()
-        for eng in engs:
-            launch(eng, timed=True)
+        launch_all(timed=True)
         b.record()
+    if shared:
+        for eng in engs:
+            eng.shared_q_flush()                                          # the last synchronisations end inside the timed region
     stop.record()
     cx.barrier()
     if sampler:
         sampler.mark(wall0, time.time())
     ms = start.elapsed_time(stop)
     step_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    sync_ms = float(np.mean([a.elapsed_time(b) for a, b in sync_ev])) if sync_ev else 0.0
-    kern_ms = (step_ms - sync_ms * parts) / parts                         # mean duration of ONE k_run launch
+    sync_ms = 0.0
+    if shared:                                                            # the synchronisation alone (not overlapped), for the record
+        for i in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            engs[0].shared_q_sync(cx.dist)
+            b.record()
+            if i:
+                sync_ev.append((a, b))
+        torch.cuda.synchronize()
+        sync_ms = float(np.mean([a.elapsed_time(b) for a, b in sync_ev]))
+    kern_ms = step_ms / (1 if streams else parts)                         # mean duration of ONE k_run launch (concurrent maps: of the step)
     t1 = totals()
     q_rows_max, state_mb = 0, 0.0
     variant = engs[0].describe_launch(backend.MODE_LEARN)
@@ -357,7 +395,7 @@ def run_block(cx: Ctx, wl: str, args, steps: int, warmup: int, sampler=None, flu
     k_bar = train_ticks / max(dec, 1)
     P = float(np.mean(np.concatenate([rm.tab.sw_P for rm in rms]))); A = float(np.mean(np.concatenate([rm.tab.sw_A for rm in rms])))
     bpd = bytes_per_decision(k_bar, P, A, A)
-    dec_per_launch = dec / cx.world / steps / parts                       # per GPU
+    dec_per_launch = dec / cx.world / steps / (1 if streams else parts)   # per GPU (concurrent maps: all launches of a step together)
     out = {"workload": desc, "value": dec / (ms / 1000.0), "unit": "decisions/s", "ms_per_step": ms / steps, "timed_region_s": ms / 1000.0,
            "steps": steps, "warmup": warmup, "ticks_per_step": ticks, "n_envs_per_gpu": B, "maps": parts, "q_cap": q_cap, "lanes_per_env": lanes,
            "kernel": variant, "kernel_ms": kern_ms, "decisions_per_launch": dec_per_launch, "train_ticks_per_decision": k_bar,
@@ -368,11 +406,13 @@ def run_block(cx: Ctx, wl: str, args, steps: int, warmup: int, sampler=None, flu
            "l2": (f"L2 flushed between the timed steps (256 MB written, inside the timed region); env state + Q tables {state_mb:.0f} MB per GPU"
                   if flushed else
                   f"inputs larger than L2: {state_mb:.0f} MB of env state + Q tables per GPU vs 126 MB L2, GBs touched per launch"),
-           "gpu_launches": steps * parts * (2 if shared else 1)}
+           "gpu_launches": steps * parts * (2 if shared else 1),
+           "concurrency": (f"{parts} launches per step on {parts} streams, concurrent" if streams else "one launch per step")}
     if shared:
-        out["collective"] = {"op": "all_reduce(sum) of int64 step sums + int32 step counts, then sfl_shared_q_apply",
+        out["collective"] = {"op": "all_reduce(sum) of int64 step sums + int32 step counts, then sfl_shared_q_apply_to",
                              "backend": "nccl" if cx.world > 1 else "none (1 GPU)", "bytes_per_step": shared_cells * 12,
-                             "ms_per_step": sync_ms, "share_of_step": sync_ms * parts / max(step_ms, 1e-9)}
+                             "schedule": "overlapped: runs on a second stream during the next launch, TD steps folded in one step late",
+                             "ms_alone": sync_ms, "share_of_step_if_not_overlapped": sync_ms / max(step_ms, 1e-9)}
     return out
 
 
@@ -495,6 +535,7 @@ def main():
     ap.add_argument("--q-cap", type=int, default=0, help="Q hash rows per environment (0 = the workload's own)")
     ap.add_argument("--lanes", type=int, default=0, help="lanes of a warp per environment (0 = library default for the batch size)")
     ap.add_argument("--cta-warps", type=int, default=0, help="warps per CTA of the hot-path kernel (0 = library default)")
+    ap.add_argument("--roomy", type=int, default=-1, help="large-map learn kernel variant: 1 = the 4-CTA/SM build, 0 = the 7-CTA/SM build, -1 = library default")
     ap.add_argument("--flush-l2", default="auto", choices=["auto", "on", "off"],
                     help="write 256 MB between the timed steps (auto: when the whole state is under 1 GiB)")
     ap.add_argument("--e2e-episodes", type=int, default=0, help="episodes per env of the end-to-end learn() call (0 = about as many ticks as the timed steps)")

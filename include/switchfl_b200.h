@@ -231,6 +231,10 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream);
  * the delta buffers are cleared.  Across GPUs the caller all-reduces shared_d and shared_c (integer sums: order
  * independent, bit-reproducible) before calling this, which leaves identical tables on every rank.                 */
 int sfl_shared_q_apply(void *ctx, void *stream);
+/* The same on explicit buffers: q_dst = q_src + mean step of (d, cnt), which are cleared.  With two tables and two
+ * accumulator pairs bound alternately (sfl_bind is a pointer swap) the all-reduce + apply of step k can run on a second
+ * stream while sfl_run of step k+1 reads the other table: see Engine.run_shared in backend.py and DESIGN.md section 6.   */
+int sfl_shared_q_apply_to(void *ctx, const void *q_src, void *q_dst, void *d, void *cnt, void *stream);
 
 /* Sum over all envs of the decisions taken (num_iter, distr_q.py:284, 361) and of the flatland ticks
  * (rail_env._elapsed_steps) after the last run: device reduction, 16-byte D2H.                         */

@@ -252,14 +252,17 @@ class DistrQLearning:
         eng = self.env.engine
         t0 = time.time()
         while True:
-            eng.run(mode, self.ticks_per_launch)
             if eng.shared_q and mode == MODE_LEARN:
-                eng.shared_q_sync(self.dist)       # every ticks_per_launch ticks: fold the mean TD steps into the table
+                eng.run_shared(self.ticks_per_launch, self.dist)    # every ticks_per_launch ticks the mean TD steps are folded in
+            else:
+                eng.run(mode, self.ticks_per_launch)
             c = eng.counters()
             if c["err"].any():
                 eng.check_errors()
             if (c["halted"] == 1).all():
                 break
+        if eng.shared_q and mode == MODE_LEARN:
+            eng.shared_q_flush()
         self.env.step_time += time.time() - t0
         self.total_decisions += int(c["decisions"].sum())
         return c
@@ -294,9 +297,10 @@ class DistrQLearning:
             self._stream_fresh = False
         else:
             eng._upload("hparams", eng.hparams)
-        eng.run(MODE_LEARN, self.ticks_per_launch if max_ticks is None else max_ticks)
         if eng.shared_q:
-            eng.shared_q_sync(self.dist)
+            eng.run_shared(self.ticks_per_launch if max_ticks is None else max_ticks, self.dist)
+        else:
+            eng.run(MODE_LEARN, self.ticks_per_launch if max_ticks is None else max_ticks)
         return eng.counters()
 
     # ------------------------------------------------------------------ distr_q.py:244-379

@@ -97,6 +97,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sfl_export_q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.c_void_p]
     lib.sfl_import_q.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.c_int, C.c_void_p]
     lib.sfl_shared_q_apply.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sfl_shared_q_apply_to.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sfl_kat_q_update.argtypes = [C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double), C.c_int]
     lib.sfl_distance_map.argtypes = [_u16p, C.c_int32, C.c_int32, _i32p, C.c_int32, _i32p, C.c_int]
     if lib.sfl_abi_version() != ABI_VERSION:
@@ -127,6 +128,11 @@ def device_q_update(rows: Sequence[Sequence[float]], device: int = 0, lib: Optio
     if rc != 0:
         raise RuntimeError(f"switchfl_b200 error {rc}: {lib.sfl_last_error().decode()}")
     return out
+
+
+def side_ok(engine) -> bool:
+    """True on a CUDA engine (streams exist); the host build of the tests runs the overlapped schedule serially."""
+    return engine.device.type == "cuda"
 
 
 def malf_threshold(rate: float) -> int:
@@ -423,23 +429,93 @@ class Engine:
         self._upload("shared_q", q)
         self.buf["shared_d"].zero_()
         self.buf["shared_c"].zero_()
+        sq = getattr(self, "_sq", None)
+        if sq is not None:                                                # the second table / accumulator pair of run_shared
+            sq["q"][1].copy_(sq["q"][0]); sq["d"][1].zero_(); sq["c"][1].zero_()
+            sq["step"], sq["done"] = 0, [None, None]
 
     def shared_q_sync(self, dist=None):
         """Fold the accumulated TD steps into the table; with an initialised ``torch.distributed`` first sum the
         accumulators over all ranks (integer all-reduce: NCCL on the GPU box, gloo in the CPU tests)."""
         assert self.shared_q
+        self._allreduce_accumulators(dist, self.buf["shared_d"], self.buf["shared_c"])
+        self._ck(self.lib.sfl_shared_q_apply(self.ctx, self._stream()))
+
+    def _allreduce_accumulators(self, dist, d_buf, c_buf):
         if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
             n = self._shared_cells()
-            d = self.buf["shared_d"][:n * 8].view(self.torch.int64)
-            c = self.buf["shared_c"][:n * 4].view(self.torch.int32)
-            dist.all_reduce(d, op=dist.ReduceOp.SUM)
-            dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        self._ck(self.lib.sfl_shared_q_apply(self.ctx, self._stream()))
+            dist.all_reduce(d_buf[:n * 8].view(self.torch.int64), op=dist.ReduceOp.SUM)
+            dist.all_reduce(c_buf[:n * 4].view(self.torch.int32), op=dist.ReduceOp.SUM)
+
+    # Overlapped schedule: two tables and two accumulator pairs.  Step k reads table T_k = buf[k % 2] and accumulates into
+    # pair k % 2; its synchronisation (all-reduce + apply) runs on a SECOND stream while the kernel of step k + 1 already
+    # reads T_{k+1}, and produces T_{k+2} = T_{k+1} + mean step of pair k % 2 in the buffer T_k occupied.  The TD steps are
+    # thus folded in one step late -- a fixed, deterministic delay (integer sums): the result does not depend on timing,
+    # on the number of ranks or on whether anything actually overlapped (the host build runs the same schedule serially).
+    def _sq_setup(self):
+        if getattr(self, "_sq", None) is None:
+            torch = self.torch
+            z = lambda n: torch.zeros(max(int(n), 16), dtype=torch.uint8, device=self.device)
+            s = self.sizes
+            self._sq = {"q": [self.buf["shared_q"], z(s.shared_q_bytes)], "d": [self.buf["shared_d"], z(s.shared_d_bytes)],
+                        "c": [self.buf["shared_c"], z(s.shared_c_bytes)], "step": 0, "done": [None, None], "side": self._side_stream()}
+            self._sq["q"][1].copy_(self._sq["q"][0])                    # T_0 = T_1 = the initial table
+        return self._sq
+
+    def _side_stream(self):
+        return self.torch.cuda.Stream(device=self.device)
+
+    def _bind_shared(self, q, d, c):
+        b = Buffers(**{k: v.data_ptr() for k, v in self.buf.items()})
+        b.shared_q, b.shared_d, b.shared_c = q.data_ptr(), d.data_ptr(), c.data_ptr()
+        self._ck(self.lib.sfl_bind(self.ctx, C.byref(b)))
+
+    def run_shared(self, max_ticks: int, dist=None, mode: int = MODE_LEARN):
+        """One step of shared-table learning on the overlapped schedule (call ``init_shared_q`` first)."""
+        assert self.shared_q
+        torch, sq = self.torch, self._sq_setup()
+        k = sq["step"] % 2
+        main, side = (torch.cuda.current_stream(self.device), sq["side"]) if side_ok(self) else (None, None)
+        if main is not None and sq["done"][k] is not None:
+            main.wait_event(sq["done"][k])                              # T_k is complete, pair k is cleared
+        self._bind_shared(sq["q"][k], sq["d"][k], sq["c"][k])
+        self.run(mode, max_ticks)
+        if main is None:                                                # host build: the same schedule, serially
+            self._allreduce_accumulators(dist, sq["d"][k], sq["c"][k])
+            self._ck(self.lib.sfl_shared_q_apply_to(self.ctx, sq["q"][1 - k].data_ptr(), sq["q"][k].data_ptr(), sq["d"][k].data_ptr(),
+                                                    sq["c"][k].data_ptr(), None))
+        else:
+            ran = torch.cuda.Event()
+            ran.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ran)
+                self._allreduce_accumulators(dist, sq["d"][k], sq["c"][k])
+                self._ck(self.lib.sfl_shared_q_apply_to(self.ctx, sq["q"][1 - k].data_ptr(), sq["q"][k].data_ptr(), sq["d"][k].data_ptr(),
+                                                        sq["c"][k].data_ptr(), C.c_void_p(side.cuda_stream)))
+                sq["done"][k] = torch.cuda.Event()
+                sq["done"][k].record(side)
+        sq["step"] += 1
+
+    def shared_q_flush(self):
+        """Wait for the outstanding synchronisations of ``run_shared`` and make the newest table the bound one."""
+        sq = getattr(self, "_sq", None)
+        if sq is None or sq["step"] == 0:
+            return
+        if side_ok(self):
+            sq["side"].synchronize()
+        newest = (sq["step"] - 1) % 2
+        if newest != 0:                                                 # keep buf["shared_q"] the table the exporters read
+            self.buf["shared_q"].copy_(sq["q"][1])
+        else:
+            sq["q"][1].copy_(sq["q"][0])
+        sq["step"], sq["done"] = 0, [None, None]
+        self._bind_shared(self.buf["shared_q"], self.buf["shared_d"], self.buf["shared_c"])
 
     def shared_q_table(self) -> np.ndarray:
         """The shared table as float64[NP, NT, 16 semaphore vectors, 3 delay levels, a_max]."""
         t, tr = self.map.tab, self.map.trains
         n = self._shared_cells()
+        self.shared_q_flush()                                             # outstanding run_shared synchronisations
         return self._download("shared_q", n * 8).view(np.float64).reshape(t.NP, len(tr.targets), 16, 3, self.sizes.a_max).copy()
 
     def export_shared_q(self, default_q: float = 0.0) -> Dict[tuple, List[float]]:

@@ -159,11 +159,15 @@ __global__ void k_sum(const sfl_env_counters *c, int n, unsigned long long *out)
   if ((threadIdx.x & 31) == 0) { atomicAdd(out, d); atomicAdd(out + 1, t); }
 }
 
-// shared-table mode: fold the mean proposed step into the table, clear the accumulators
-__global__ void k_shared_apply(double *q, long long *d, int *c, size_t n) {
+// shared-table mode: fold the mean proposed step into the table, clear the accumulators.  dst = src + mean step; src may be
+// dst (in place) or the other table of a double-buffered pair (the overlapped schedule: the kernel of the next step reads
+// src while this runs).
+__global__ void k_shared_apply(const double *src, double *dst, long long *d, int *c, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int k = c[i];
-    if (k) { q[i] += (double)d[i] / 16777216.0 / (double)k; d[i] = 0; c[i] = 0; }
+    double v = src[i];
+    if (k) { v += (double)d[i] / 16777216.0 / (double)k; d[i] = 0; c[i] = 0; }
+    if (k || src != dst) dst[i] = v;
   }
 }
 
@@ -712,21 +716,36 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   return SFL_OK;
 }
 
+static int shared_apply(Ctx *c, const double *src, double *dst, long long *d, int *cn, void *stream) {
+  const size_t n = (size_t)c->m.NP * c->m.NT * 48u * (size_t)c->L.a_max;
+#ifndef SFL_HOST_EMUL
+  k_shared_apply<<<c->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(src, dst, d, cn, n);
+  CU(cudaGetLastError());
+#else
+  (void)stream;
+  for (size_t i = 0; i < n; i++) {
+    double v = src[i];
+    if (cn[i]) { v += (double)d[i] / 16777216.0 / (double)cn[i]; d[i] = 0; cn[i] = 0; }
+    dst[i] = v;
+  }
+#endif
+  return SFL_OK;
+}
+
 int sfl_shared_q_apply(void *ctx, void *stream) {
   Ctx *c = (Ctx *)ctx;
   if (!c || !c->bound) return fail(SFL_E_STATE, "sfl_bind first%s");
   DeviceGuard dg(c->device);
   if (!c->cfg.shared_q) return fail(SFL_E_STATE, "context was not created in shared-table mode%s");
-  const size_t n = (size_t)c->m.NP * c->m.NT * 48u * (size_t)c->L.a_max;
-  double *q = (double *)c->bufs.shared_q; long long *d = (long long *)c->bufs.shared_d; int *cn = (int *)c->bufs.shared_c;
-#ifndef SFL_HOST_EMUL
-  k_shared_apply<<<c->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(q, d, cn, n);
-  CU(cudaGetLastError());
-#else
-  (void)stream;
-  for (size_t i = 0; i < n; i++) if (cn[i]) { q[i] += (double)d[i] / 16777216.0 / (double)cn[i]; d[i] = 0; cn[i] = 0; }
-#endif
-  return SFL_OK;
+  return shared_apply(c, (const double *)c->bufs.shared_q, (double *)c->bufs.shared_q, (long long *)c->bufs.shared_d, (int *)c->bufs.shared_c, stream);
+}
+
+int sfl_shared_q_apply_to(void *ctx, const void *q_src, void *q_dst, void *d, void *cnt, void *stream) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || !q_src || !q_dst || !d || !cnt) return fail(SFL_E_ARG, "null argument%s");
+  if (!c->cfg.shared_q) return fail(SFL_E_STATE, "context was not created in shared-table mode%s");
+  DeviceGuard dg(c->device);
+  return shared_apply(c, (const double *)q_src, (double *)q_dst, (long long *)d, (int *)cnt, stream);
 }
 
 int sfl_total_decisions(void *ctx, uint64_t *decisions, uint64_t *ticks, void *stream) {

@@ -48,6 +48,9 @@ class EmulEngine(backend.Engine):
     def _stream(self):
         return None
 
+    def _side_stream(self):
+        return None
+
     def _upload(self, name, host):
         raw = np.ascontiguousarray(host).view(np.uint8).reshape(-1)
         self.h2d_bytes += raw.size

@@ -371,7 +371,8 @@ def _bench_variants():
     for wl, (fixture, envs, q_cap, _) in bench.WORKLOADS.items():
         fxs = bench.workload_fixtures(bench.fixture_path(fixture))
         per_map = envs // len(fxs)
-        eng = backend.Engine(backend.RailMap(fxs[0]), n_envs=per_map, q_cap=q_cap, ep_cap=4, shared_q=(wl == "c5"), bind=False)
+        eng = backend.Engine(backend.RailMap(fxs[0]), n_envs=per_map, q_cap=q_cap, ep_cap=4, shared_q=(wl == "c5"), bind=False,
+                             **bench.engine_kwargs(len(fxs)))
         out[wl] = eng.kernel_variant(backend.MODE_LEARN)
         eng.close()
     return out
@@ -448,3 +449,18 @@ def test_cuda_free_running_learn_equals_the_host_build(name):
 def test_cuda_reapply_q_init():
     from tests.test_emul_parity import check_reapply_q_init
     check_reapply_q_init(backend.Engine)
+
+
+def test_cuda_shared_table_overlapped_schedule_equals_the_serial_host_run():
+    """run_shared on the device -- all-reduce + apply on a second stream while the next launch runs -- gives exactly the
+    table the host build gives running the same schedule serially: the overlap changes timing, not results."""
+    from tests.emulated import EmulEngine
+    from tests.test_host_api import _shared_run
+    fx, _ = load_golden("slips24_t6")
+    rm = backend.RailMap(fx)
+    seeds = list(range(1, 40))
+    dev = _shared_run(rm, None, seeds, launches=7, ticks=48, overlapped=True, cls=backend.Engine)
+    host = _shared_run(rm, None, seeds, launches=7, ticks=48, overlapped=True, cls=EmulEngine)
+    assert np.array_equal(dev.counters()["decisions"], host.counters()["decisions"])
+    assert np.array_equal(dev.shared_q_table(), host.shared_q_table())
+    dev.close(); host.close()

@@ -278,15 +278,20 @@ def test_grid_launcher_writes_the_reference_tree():
 HP_SHARED = dict(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0)
 
 
-def _shared_run(rm, emul, seeds, launches=5, ticks=64, dist=None):
-    eng = EmulEngine(rm, n_envs=len(seeds), q_cap=2, ep_cap=4, shared_q=True)
+def _shared_run(rm, emul, seeds, launches=5, ticks=64, dist=None, overlapped=False, cls=None):
+    eng = (cls or EmulEngine)(rm, n_envs=len(seeds), q_cap=2, ep_cap=4, shared_q=True)
     eng.set_hparams(**HP_SHARED, seeds=seeds, episodes=-1)
     eng.reset()
     eng.init_shared_q(0.0)
     for _ in range(launches):
-        eng.run(backend.MODE_LEARN, ticks)
+        if overlapped:                                   # two tables / accumulator pairs, TD steps folded in one step late
+            eng.run_shared(ticks, dist)
+        else:
+            eng.run(backend.MODE_LEARN, ticks)
+            eng.shared_q_sync(dist)
         eng.check_errors()
-        eng.shared_q_sync(dist)
+    if overlapped:
+        eng.shared_q_flush()
     return eng
 
 
@@ -314,6 +319,25 @@ def test_shared_table_mode_is_deterministic_and_averages():
     assert (mixed.counters()["q_rows"] == 0).all()
 
 
+def test_shared_table_overlapped_schedule_properties():
+    """run_shared (double-buffered tables, synchronisation one step late): deterministic, N identical environments leave
+    the table one leaves, and the delay really changes the trajectory (it is not the synchronous schedule in disguise)."""
+    emul = build_emul()
+    fx, _ = load_golden("slips24_t6")
+    rm = backend.RailMap(fx)
+    q1 = _shared_run(rm, emul, [7], overlapped=True).shared_q_table()
+    assert np.array_equal(q1, _shared_run(rm, emul, [7], overlapped=True).shared_q_table())
+    assert np.array_equal(q1, _shared_run(rm, emul, [7, 7, 7], overlapped=True).shared_q_table())
+    mixed = _shared_run(rm, emul, [1, 2, 3, 4, 5, 6], overlapped=True)
+    qm = mixed.shared_q_table()
+    assert np.isfinite(qm).all() and not np.array_equal(qm, q1)
+    assert not np.array_equal(qm, _shared_run(rm, emul, [1, 2, 3, 4, 5, 6]).shared_q_table())
+    # a further run continues from the flushed table on both buffers
+    mixed.run_shared(64)
+    mixed.shared_q_flush()
+    assert np.isfinite(mixed.shared_q_table()).all() and (mixed.buf["shared_c"].numpy() == 0).all()
+
+
 _SHARED_WORKER = r'''
 import os, sys, json
 import numpy as np
@@ -329,24 +353,27 @@ dist.init_process_group("gloo", rank=rank, world_size=ws)
 fx = mapgen.load_fixture(os.path.join(sys.argv[1], "tests", "golden", "slips24_t6.fixture.npz"))
 rm = backend.RailMap(fx)
 lo, hi = sharding.shard_range(6, rank, ws)
-eng = _shared_run(rm, sys.argv[2], list(range(1 + lo, 1 + hi)), dist=dist)
+eng = _shared_run(rm, sys.argv[2], list(range(1 + lo, 1 + hi)), dist=dist, overlapped=len(sys.argv) > 4)
 np.save(os.path.join(sys.argv[3], f"q{rank}.npy"), eng.shared_q_table())
 dist.destroy_process_group()
 '''
 
 
-def test_shared_table_two_ranks_allreduce_equals_one_process():
+@pytest.mark.parametrize("overlapped", [False, True])
+def test_shared_table_two_ranks_allreduce_equals_one_process(overlapped):
     """Two ranks with three environments each, accumulators all-reduced (gloo) before every apply: both ranks end with
-    the table one process with all six environments ends with, bit for bit."""
+    the table one process with all six environments ends with, bit for bit -- on the synchronous and on the overlapped
+    (one step late) schedule."""
     emul = build_emul()
     fx, _ = load_golden("slips24_t6")
     rm = backend.RailMap(fx)
-    want = _shared_run(rm, emul, [1, 2, 3, 4, 5, 6]).shared_q_table()
+    want = _shared_run(rm, emul, [1, 2, 3, 4, 5, 6], overlapped=overlapped).shared_q_table()
     with tempfile.TemporaryDirectory() as tmp:
         w = os.path.join(tmp, "w.py")
         open(w, "w").write(_SHARED_WORKER)
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                              "--master-port", "29543", w, ROOT, emul, tmp], capture_output=True, text=True, timeout=600)
+                              "--master-port", "29543" if not overlapped else "29545", w, ROOT, emul, tmp] + (["overlapped"] if overlapped else []),
+                             capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stderr[-2000:]
         q0, q1 = np.load(os.path.join(tmp, "q0.npy")), np.load(os.path.join(tmp, "q1.npy"))
     assert np.array_equal(q0, q1) and np.array_equal(q0, want)
