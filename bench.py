@@ -498,7 +498,7 @@ def run_ours(args):
                          "achieved_warp_inst_per_s": kc["warp_inst_per_decision"] * dps_gpu, "peak_warp_inst_per_s": 148 * 4 * sm_hz,
                          "frac": kc["warp_inst_per_decision"] * dps_gpu / (148 * 4 * sm_hz),
                          "source": kc.get("source", "") + " (committed ncu capture, NOT this run); peak = 148 SMs x 4 schedulers x SM clock"}
-    cfg = {k: main[k] for k in ("workload", "n_envs_per_gpu", "maps", "ticks_per_step", "q_cap", "lanes_per_env", "kernel",
+    cfg = {k: main[k] for k in ("workload", "n_envs_per_gpu", "maps", "ticks_per_step", "q_cap", "lanes_per_env", "kernel", "decisions_per_launch",
                                 "train_ticks_per_decision", "ticks", "episodes", "trains", "arrived_trains_per_episode",
                                 "forced_stop_share", "stop_action_share", "abandoned_episode_share", "q_rows_max", "l2", "timed_region_s")}
     cfg["sharding"] = ("envs by seed range, no data-path collective" if wl != "c5" else
