@@ -22,6 +22,8 @@
 #define SFL_DEV 1
 #define SFL_FN __device__ __forceinline__
 #define SFL_NI __device__ __forceinline__
+#define SFL_RARE __device__ __noinline__          // once-per-episode paths: out of line (instruction cache), even though a
+                                                  // noinline callee reads the kernel parameter block through a generic pointer
 #define SFL_CONST __constant__
 #define SFL_NU _Pragma("unroll 1")
 #define SFL_U4 _Pragma("unroll 4")
@@ -32,6 +34,7 @@
 #include <string.h>
 #define SFL_FN inline
 #define SFL_NI inline
+#define SFL_RARE inline
 #define SFL_CONST static
 #define SFL_NU
 #define SFL_U4
@@ -321,6 +324,25 @@ SFL_FN int port_blocked(Env e, int next_port, int out_port, int me, int now) {
 // Row = [key+1 as u64 bits | A_max doubles]; open addressing, linear probing, no deletion.  A row is created
 // exactly where the reference's __check_entry (distr_q.py:47-57) would insert a dict entry, so the exported
 // key set equals the reference's.
+// insertion of a new row (rare once the tables are warm): out of line
+template <class Env>
+SFL_RARE void q_insert(SFL_K, Env e, const Hp hp, unsigned key, double *row) {
+  *(unsigned long long *)row = (unsigned long long)key + 1ull;
+  e.h()->q_rows++;
+  unsigned per_port = (unsigned)(c_L.NT * 48);
+  int port = (int)(key / per_port);
+  int A = c_m.sw[c_m.port[port].w].y;
+  double dq = hp->default_q;
+  SFL_NU
+  for (int a = 0; a < A; a++) row[1 + a] = dq;
+  if (c_ra.q_init_on) {                                   // distr_q.py:81-181 (lazy: same values, created on first touch)
+    unsigned rem = key - (unsigned)port * per_port;
+    int tgt = (int)(rem / 48u), semb = (int)((rem % 48u) / 3u);
+    int qi = c_m.qinit[port * c_L.NT + tgt];
+    if (qi >= 0 && semb != 0) row[1 + (qi & 15)] = (qi & 16) ? 1000.0 : 500.0;
+  }
+}
+
 template <class Env>
 SFL_NI double *q_row(SFL_K, Env e, const Hp hp, unsigned key) {
   if (Env::SQ) return c_ra.sq_q + (size_t)key * c_L.a_max;              // shared-table mode: dense, initialised by the host
@@ -334,20 +356,7 @@ SFL_NI double *q_row(SFL_K, Env e, const Hp hp, unsigned key) {
     if (k == (unsigned long long)key + 1ull) return row + 1;
     if (k == 0ull) {
       if (e.h()->q_rows >= c_L.q_cap - 1) break;
-      *(unsigned long long *)row = (unsigned long long)key + 1ull;
-      e.h()->q_rows++;
-      unsigned per_port = (unsigned)(c_L.NT * 48);
-      int port = (int)(key / per_port);
-      int A = c_m.sw[c_m.port[port].w].y;
-      double dq = hp->default_q;
-      SFL_NU
-      for (int a = 0; a < A; a++) row[1 + a] = dq;
-      if (c_ra.q_init_on) {                                   // distr_q.py:81-181 (lazy: same values, created on first touch)
-        unsigned rem = key - (unsigned)port * per_port;
-        int tgt = (int)(rem / 48u), semb = (int)((rem % 48u) / 3u);
-        int qi = c_m.qinit[port * c_L.NT + tgt];
-        if (qi >= 0 && semb != 0) row[1 + (qi & 15)] = (qi & 16) ? 1000.0 : 500.0;
-      }
+      q_insert(K, e, hp, key, row);
       return row + 1;
     }
     i++;
@@ -753,7 +762,7 @@ SFL_FN void decide(SFL_K, Env e, const Hp hp, int env_id, int t) {
 // switch_env.py:93-158 with a constant map: state re-init + the precomputed _init_ports table (:507-568)
 // (`on`: this group resets; the syncs are the whole warp's)
 template <int G, class Env>
-SFL_NI void env_reset(SFL_K, Env e, const Grp<G> &g, int on) {
+SFL_RARE void env_reset(SFL_K, Env e, const Grp<G> &g, int on) {
   EnvHdr *h = e.h();
   const int T = on ? c_L.T : 0, NP = on ? c_L.NP : 0;
   SFL_NU
@@ -1076,7 +1085,7 @@ SFL_FN void env_tick(SFL_K, Env e, Scratch sc, const Hp hp, int env_id, const Gr
 
 // ------------------------------------------------------------------------------------------------ episode end
 template <class Env>
-SFL_NI void episode_end(SFL_K, Env e, int env_id) {   // first lane
+SFL_RARE void episode_end(SFL_K, Env e, int env_id) {   // first lane
   EnvHdr *h = e.h();
   if (c_ra.ep_log && h->n_ep_logged < c_ra.ep_cap) {
     sfl_ep_rec *rec = c_ra.ep_log + (size_t)env_id * c_ra.ep_cap + h->n_ep_logged;
