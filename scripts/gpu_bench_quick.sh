@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: scripts/gpu_bench_quick.sh <tag> [extra bench args]  -- short bench lines only (no tests): value / kernel ms per workload
 tag=$1; shift
-python bench.py --steps 6 --warmup 3 --no-cpu --e2e-episodes 4 "$@" > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+timeout 150 python bench.py --steps 6 --warmup 3 --no-cpu --e2e-episodes 4 "$@" > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 python - <<PY
 import json
 try:

@@ -1,8 +1,8 @@
 #!/bin/bash
 # usage: scripts/gpu_quick.sh <tag> [pytest -k expr]  -- GPU parity tests + short bench lines of every workload (value, e2e, kernel ms)
 tag=$1
-python -m pytest tests -m gpu -q -x ${2:+-k "$2"} 2>&1 | tail -8 > gpurun_out/${tag}_gputest.log
-python bench.py --steps 6 --warmup 3 --no-cpu --e2e-episodes 8 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+timeout 400 python -m pytest tests -m gpu -q -x ${2:+-k "$2"} 2>&1 | tail -8 > gpurun_out/${tag}_gputest.log
+timeout 150 python bench.py --steps 6 --warmup 3 --no-cpu --e2e-episodes 8 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 python - <<PY
 import json
 try:

@@ -3,7 +3,7 @@
 tag=$1; wl=$2; shift 2
 i=0
 for a in "$@"; do
-  python bench.py --workload $wl --steps 6 --warmup 3 --no-cpu --extra= --e2e-episodes 1 $a > gpurun_out/${tag}_$i.json 2> gpurun_out/${tag}_$i.err
+  timeout 150 python bench.py --workload $wl --steps 6 --warmup 3 --no-cpu --extra= --e2e-episodes 1 $a > gpurun_out/${tag}_$i.json 2> gpurun_out/${tag}_$i.err
   python -c "
 import json,sys
 try:
