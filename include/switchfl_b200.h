@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SFL_ABI_VERSION 5
+#define SFL_ABI_VERSION 6
 
 enum {
   SFL_OK = 0,
@@ -140,6 +140,9 @@ typedef struct sfl_env_counters {      /* written by sfl_run for every env      
   uint64_t stop_actions;                    /* decisions that chose STOP                                                   */
   uint64_t arrived_trains;                  /* trains at their destination, summed over the finished episodes (distr_q.py:364) */
   uint64_t reserved2;
+  uint64_t phase_cycles[6];                 /* sfl_set_phase_clock: SM cycles spent per phase -- 0 train ticks (rail_env.step + _move_trains
+                                               bookkeeping), 1 observe (last()), 2 action selection, 3 apply + reward (rest of step()),
+                                               4 Q-update, 5 episode reset: the split behind the timers main.py:72-78 prints     */
 } sfl_env_counters;
 
 typedef struct sfl_dec_rec {           /* one switch-agent decision (trace)                           */
@@ -209,6 +212,10 @@ int sfl_set_cta_warps(void *ctx, int warps);
 /* Compile-time variant of the large-map learn kernel: 1 = the one built for 4 CTAs per SM (more registers), 0 = the one
  * for 7, -1 = automatic (roomy when the launch fits one wave anyway).  A scheduling choice only.                   */
 int sfl_set_roomy(void *ctx, int roomy);
+/* Per-phase cycle counters (sfl_env_counters.phase_cycles) for the wall-clock breakdown main.py:68-78 prints
+ * (switch_env.py:67-73 accumulators).  Instrumented runs use the full kernel (the one that also carries the traces);
+ * off by default: the production kernels carry no clock reads.                                                       */
+int sfl_set_phase_clock(void *ctx, int on);
 /* Which kernel instantiation and launch configuration sfl_run(mode) would use now (traced != 0: with decision / tick
  * traces), as text: "k_run<G=..,KIND=..,TH=..,SQ=..,ONE=..,ROOMY=..> grid=.. block=.. smem=..".  No counterpart in the
  * reference; it lets the parity tests name -- and force, with sfl_set_lanes / sfl_set_roomy -- exactly the

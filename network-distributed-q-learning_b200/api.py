@@ -101,13 +101,16 @@ class ASyncSwitchEnv:
 
     def __init__(self, rail_env: RailEnv, max_steps: int = 200, render_mode=None, observer=None, seed=None,
                  n_envs: int = 1, device: str = "cuda:0", q_cap: Optional[int] = None, ep_cap: int = 128, shared_q: bool = False,
-                 _engine_kwargs=None):
+                 phase_timers: bool = False, _engine_kwargs=None):
+        """``phase_timers``: run the instrumented kernel (per-phase cycle counters, a few per cent slower) so that all seven
+        wall-clock accumulators of switch_env.py:67-73 are filled; without it the fused kernel books its whole time on
+        ``step_time`` (and resets on ``reset_total_time``)."""
         self.rail_env = rail_env
         self.max_steps = max_steps
         self.render_mode = render_mode
         self.seed = seed
         self.n_envs = int(n_envs)
-        kw = dict(act_cap=1, shared_q=shared_q)
+        kw = dict(act_cap=1, shared_q=shared_q, phase_clock=bool(phase_timers))
         kw.update(_engine_kwargs or {})
         self.rail_map = RailMap(rail_env.fixture, device_bfs=self.engine_cls.bfs_device(device))
         self.possible_agents = self.rail_map.tab.switch_names()          # switch_env.py:51-52
@@ -263,7 +266,16 @@ class DistrQLearning:
                 break
         if eng.shared_q and mode == MODE_LEARN:
             eng.shared_q_flush()
-        self.env.step_time += time.time() - t0
+        dt = time.time() - t0
+        self.env.step_time += dt
+        if getattr(eng, "phase_clock", False):
+            # switch_env.py:67-73: split the kernel time by the per-phase cycle counters of the instrumented kernel
+            ph = c["phase_cycles"].astype(np.float64).sum(axis=0)
+            if ph.sum() > 0:
+                sh = ph / ph.sum()
+                env = self.env
+                env.flatland_step_time += dt * sh[0]; env.last_time += dt * sh[1]; env.action_selection_time += dt * sh[2]
+                env.update_time += dt * sh[4]; env.reset_time += dt * sh[5]
         self.total_decisions += int(c["decisions"].sum())
         return c
 

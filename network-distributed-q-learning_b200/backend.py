@@ -18,7 +18,7 @@ from . import railmap
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libswitchfl_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MODE_LEARN, MODE_GREEDY, MODE_REPLAY, MODE_STEP = 0, 1, 2, 3
 ERR_NO_TRAIN_AT_SWITCH = 1
 ERR_BITS = {1: "no train at active switch (observer.py:294-307)", 2: "infinite distance to target (observer.py:35-36)",
@@ -63,14 +63,15 @@ HPARAMS_DT = np.dtype([("gamma", "f8"), ("epsilon", "f8"), ("epsilon_decay_rate"
 COUNTERS_DT = np.dtype([("decisions", "u8"), ("ticks", "u8"), ("train_ticks", "u8"), ("episodes", "i4"), ("err", "i4"),
                         ("q_rows", "i4"), ("halted", "i4"), ("n_dec_logged", "i4"), ("n_tick_logged", "i4"),
                         ("n_ep_logged", "i4"), ("elapsed", "i4"), ("aborted", "i4"), ("reserved", "i4"),
-                        ("forced_stops", "u8"), ("stop_actions", "u8"), ("arrived_trains", "u8"), ("reserved2", "u8")])
+                        ("forced_stops", "u8"), ("stop_actions", "u8"), ("arrived_trains", "u8"), ("reserved2", "u8"),
+                        ("phase_cycles", "u8", (6,))])
 DEC_DT = np.dtype([("ep", "i4"), ("tick", "i4"), ("sw", "i4"), ("train", "i4"), ("key", "u4"), ("mask", "i4"), ("action", "i4"),
                    ("next_sw", "i4"), ("reward", "i4"), ("done", "i4"), ("arrived", "u8")])
 TICK_DT = np.dtype([("pos", "i4"), ("dir", "i1"), ("state", "i1"), ("malf", "i2")])
 STEP_DT = np.dtype([("pending", "i4"), ("sw", "i4"), ("train", "i4"), ("key", "u4"), ("mask", "i4"), ("done", "i4"), ("elapsed", "i4"),
                     ("last_next_sw", "i4"), ("arrived", "u8"), ("rewards", "i4", (64,))])
 EP_DT = np.dtype([("cum_reward", "f8"), ("decisions", "i4"), ("arrived", "i4"), ("num_malfunctions", "i4"), ("ticks", "i4"), ("arrived_mask", "u8")])
-assert HPARAMS_DT.itemsize == 80 and COUNTERS_DT.itemsize == 96 and DEC_DT.itemsize == 48 and TICK_DT.itemsize == 8 and EP_DT.itemsize == 32
+assert HPARAMS_DT.itemsize == 80 and COUNTERS_DT.itemsize == 144 and DEC_DT.itemsize == 48 and TICK_DT.itemsize == 8 and EP_DT.itemsize == 32
 
 
 def load_library(path: Optional[str] = None) -> C.CDLL:
@@ -91,6 +92,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.sfl_get_lanes.argtypes = [C.c_void_p]
     lib.sfl_set_cta_warps.argtypes = [C.c_void_p, C.c_int]
     lib.sfl_set_roomy.argtypes = [C.c_void_p, C.c_int]
+    lib.sfl_set_phase_clock.argtypes = [C.c_void_p, C.c_int]
     lib.sfl_describe_launch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int]
     lib.sfl_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.sfl_total_decisions.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
@@ -242,7 +244,7 @@ class Engine:
     def __init__(self, rail_map: RailMap, n_envs: int, device: str = "cuda:0", q_cap: int = 1024, pend_cap: int = 8,
                  max_steps: int = 100_000, dec_cap: int = 0, tick_cap: int = 0, ep_cap: int = 64, act_cap: int = 0,
                  ev_cap: int = 0, trace_sem: bool = False, lanes: Optional[int] = None, shared_q: bool = False,
-                 cta_warps: Optional[int] = None, roomy: Optional[bool] = None, bind: bool = True):
+                 cta_warps: Optional[int] = None, roomy: Optional[bool] = None, phase_clock: bool = False, bind: bool = True):
         """``bind=False`` creates the context only (no device buffers): enough for ``describe_launch``."""
         import torch
         self.torch = torch
@@ -263,6 +265,9 @@ class Engine:
             self._ck(self.lib.sfl_set_cta_warps(self.ctx, int(cta_warps)))
         if roomy is not None:
             self._ck(self.lib.sfl_set_roomy(self.ctx, int(bool(roomy))))
+        if phase_clock:
+            self._ck(self.lib.sfl_set_phase_clock(self.ctx, 1))
+        self.phase_clock = bool(phase_clock)
         self.hparams = np.zeros(self.n_envs, HPARAMS_DT)
         self._pinned = {}
         self._pinned_ev = {}

@@ -247,6 +247,7 @@ struct Ctx {
   Layout L;
   sfl_config cfg;
   sfl_buffers bufs;
+  int phase_clock;     // per-phase cycle counters: instrumented launches use the full kernel
   int bound, device, q_init_on, lanes, sm_count, cta_warps, roomy;        // roomy: -1 automatic, 0 / 1 forced
   unsigned hot_bytes, env_smem, tail_hot;
   void *blob;          // device block holding every map table
@@ -475,7 +476,7 @@ int sfl_create(const sfl_map_desc *map, const sfl_config *cfg, int device, void 
   DeviceGuard dg(device);
   Ctx *c = new (std::nothrow) Ctx();
   if (!c) return fail(SFL_E_NOMEM, "host alloc%s");
-  c->L = L; c->cfg = *cfg; c->bound = 0; c->device = device; c->q_init_on = 0; c->cta_warps = 0; c->roomy = -1; c->blob = nullptr; c->sum_buf = nullptr; c->sm_count = sm_count;
+  c->L = L; c->cfg = *cfg; c->bound = 0; c->device = device; c->q_init_on = 0; c->cta_warps = 0; c->roomy = -1; c->phase_clock = 0; c->blob = nullptr; c->sum_buf = nullptr; c->sm_count = sm_count;
   memset(&c->bufs, 0, sizeof(c->bufs));
   auto pcell = [&](int cell) { return cell < 0 ? -1 : (cell / W + 1) * Wp + (cell % W + 1); };
   // ---- pack every table into one host image, 16-byte aligned sections
@@ -600,10 +601,18 @@ int sfl_set_roomy(void *ctx, int roomy) {
   return SFL_OK;
 }
 
+int sfl_set_phase_clock(void *ctx, int on) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c) return fail(SFL_E_ARG, "null ctx%s");
+  if (on && c->cfg.shared_q) return fail(SFL_E_ARG, "shared-table mode has no instrumented kernel%s");
+  c->phase_clock = on ? 1 : 0;
+  return SFL_OK;
+}
+
 int sfl_describe_launch(void *ctx, int mode, int traced, char *buf, int cap) {
   Ctx *c = (Ctx *)ctx;
   if (!c || !buf || cap < 1) return fail(SFL_E_ARG, "null argument%s");
-  const int trace = traced || mode == SFL_MODE_STEP || mode == SFL_MODE_REPLAY;
+  const int trace = traced || mode == SFL_MODE_STEP || mode == SFL_MODE_REPLAY || c->phase_clock;
   const int kind = trace ? K_FULL : (mode == SFL_MODE_GREEDY ? K_GREEDY : K_LEARN);
   LaunchPlan lp;
   if (plan_launch(c, kind, &lp)) return SFL_E_ARG;
@@ -690,7 +699,8 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   // recorded malfunction events replace the Philox draws in replay mode, and in greedy / step mode when a schedule was bound (ev_cap > 0)
   ra.replay_ev = (mode != SFL_MODE_LEARN && c->cfg.ev_cap > 0) ? (const int *)c->bufs.replay_ev : nullptr;
   // learn and greedy without traces run the two specialised kernels; replay, step and traced runs the full one
-  const int trace = ra.trace_dec || ra.trace_tick || mode == SFL_MODE_STEP || mode == SFL_MODE_REPLAY;
+  ra.phase_clock = c->phase_clock;
+  const int trace = ra.trace_dec || ra.trace_tick || mode == SFL_MODE_STEP || mode == SFL_MODE_REPLAY || c->phase_clock;
   const int kind = trace ? K_FULL : (mode == SFL_MODE_GREEDY ? K_GREEDY : K_LEARN);
 #ifndef SFL_HOST_EMUL
   LaunchPlan lp;

@@ -146,6 +146,7 @@ struct EnvHdr {            // 128 bytes at the start of every env block
   unsigned eps_z, eps_w;               //   words 2 and 3 of that pair's Philox block (the odd decision of the pair uses them)
   unsigned long long forced_stops, stop_actions, arrived_trains;     // lifetime statistics (sfl_env_counters)
   unsigned long long pad_;
+  unsigned long long ph[6], ph_t0;      // phase clock (full kernel, sfl_set_phase_clock): cycles per phase, start of the running one
 };
 
 // Per-train records (16 bytes each, one vector load per phase):
@@ -160,7 +161,7 @@ struct SwS { int ninter, pad; double eps_pow; };
 
 struct RunArgs {           // per-launch arguments
   int mode, max_ticks, n_envs, trace_sem;
-  int dec_cap, tick_cap, ep_cap, act_cap, ev_cap, max_steps, q_init_on, pad1;
+  int dec_cap, tick_cap, ep_cap, act_cap, ev_cap, max_steps, q_init_on, phase_clock;
   unsigned hot_bytes, env_smem, tail_hot, pad2;
   char *state;
   const sfl_hparams *hp;
@@ -245,6 +246,16 @@ struct Hp {
   hot_t o;
   SFL_FN const sfl_hparams *operator->() const { return (const sfl_hparams *)hot_ptr(o); }
 };
+
+// phase clock (instrumented runs of the full kernel only): the first lane charges the cycles since the last mark to a phase
+#if SFL_DEV
+SFL_FN unsigned long long sm_clock() { return (unsigned long long)clock64(); }
+#else
+SFL_FN unsigned long long sm_clock() { return 0ull; }
+#endif
+enum { PH_TICK = 0, PH_OBSERVE = 1, PH_ACT = 2, PH_APPLY = 3, PH_UPDATE = 4, PH_RESET = 5 };
+#define SFL_PHASE_START(h) do { if (TRACE && c_ra.phase_clock) (h)->ph_t0 = sm_clock(); } while (0)
+#define SFL_PHASE_MARK(h, i) do { if (TRACE && c_ra.phase_clock) { const unsigned long long t_ = sm_clock(); (h)->ph[i] += t_ - (h)->ph_t0; (h)->ph_t0 = t_; } } while (0)
 
 // ------------------------------------------------------------------------------------------------ kernel kinds
 // The run mode is a compile-time property of the two production kernels (learn, greedy): with the mode a runtime
@@ -515,6 +526,7 @@ SFL_FN void finish_decision(SFL_K, Env e, const Hp hp, int env_id) {
   const bool TRACE = KIND == K_FULL;
   const int mode = run_mode<KIND>(K);
   EnvHdr *h = e.h();
+  SFL_PHASE_START(h);
   if (mode == SFL_MODE_LEARN || mode == SFL_MODE_REPLAY) {
     unsigned long long fresh = h->done_mask & ~h->at_dest_mask;
     SFL_NU
@@ -536,6 +548,7 @@ SFL_FN void finish_decision(SFL_K, Env e, const Hp hp, int env_id) {
     ss->eps_pow = dmul(ss->eps_pow, hp->epsilon_decay_rate);
   }
   h->pending_fin = -1;
+  SFL_PHASE_MARK(h, PH_UPDATE);
   if (h->step_counter > c_ra.max_steps) h->truncated = 1;
   if (TRACE) {
     if (c_ra.trace_dec && h->cur_dec >= 0 && h->cur_dec < c_ra.dec_cap) {
@@ -597,6 +610,7 @@ SFL_FN void decide(SFL_K, Env e, const Hp hp, int env_id, int t) {
   const int mode = run_mode<KIND>(K);
   EnvHdr *h = e.h();
   const int now = h->elapsed;
+  SFL_PHASE_START(h);
   int4 ta = e.tra()[t], tb = e.trb()[t];
   // What does not depend on the observation is loaded before it, so that these round trips to HBM overlap with the port
   // checks instead of following them one by one: last()'s reward, epsilon's decay product, the head of the pending list
@@ -619,6 +633,7 @@ SFL_FN void decide(SFL_K, Env e, const Hp hp, int env_id, int t) {
   const int4 tr0 = c_m.train0[t], tr1 = c_m.train1[t];
   const int pos = ta.x, dir = ta.y & 0xFF, st = (ta.y >> 8) & 0xFF;
   const int my_port = (int)((unsigned)ta.w >> 16);
+  SFL_PHASE_MARK(h, PH_OBSERVE);
   // ---- act (distr_q.py:312-320 / :211)
   double *my_row = nullptr;
   int action = -1;
@@ -663,6 +678,7 @@ SFL_FN void decide(SFL_K, Env e, const Hp hp, int env_id, int t) {
     my_row = q_row(K, e, hp, key);
     action = max_action(my_row, A, mask);
   }
+  SFL_PHASE_MARK(h, PH_ACT);
   // ---- apply (switch_env.py:203-294, switch_agents.py:136-168)
   int moving = 0, move2 = A_STOP, in_port = my_port, out_port = my_port;
   if (action != A - 1) {
@@ -708,6 +724,7 @@ SFL_FN void decide(SFL_K, Env e, const Hp hp, int env_id, int t) {
   e.rewards()[next_switch * c_L.T + t] = reward_out;                              // switch_env.py:289
   tb.z = curr;                                                                    // switch_env.py:291
   h->step_counter++;
+  SFL_PHASE_MARK(h, PH_APPLY);
   // ---- learn (distr_q.py:329-342)
   if (learning) {
     int n = (tb.y >> 16) & 0xFF;
@@ -739,6 +756,7 @@ SFL_FN void decide(SFL_K, Env e, const Hp hp, int env_id, int t) {
     tb.y = (tb.y & 0xFFFF) | (n << 16);
   }
   e.trb()[t] = tb;
+  SFL_PHASE_MARK(h, PH_UPDATE);
   h->cum_reward += (double)reward_in;                                             // distr_q.py:360
   if (TRACE) {
     if (c_ra.trace_dec) {
@@ -1223,11 +1241,15 @@ SFL_FN void env_run(SFL_K, int env_id, unsigned stage, char *host_scratch) {
     if (any_reset) {
       if (live && need_reset && hp->episodes >= 0 && h->episode >= hp->episodes) live = 0;      // halt: need_reset stays set
       const int on = live && need_reset;
+      if (on && g.gl == 0) SFL_PHASE_START(h);
       env_reset<G>(K, e, g, on);
+      if (on && g.gl == 0) SFL_PHASE_MARK(h, PH_RESET);
       if (on) { need_reset = 0; R.elapsed = 0; R.ended = 0; R.rng_blk = -1; R.active = 0; R.done = 0; }
       any_reset = 0;
     }
+    if (live && !paused && g.gl == 0) SFL_PHASE_START(h);
     env_tick<G, KIND, ONE>(K, e, sc, hp, env_id, g, R, live && !paused);
+    if (live && !paused && g.gl == 0) SFL_PHASE_MARK(h, PH_TICK);
   }
   g.sync();
   if (valid && g.gl == 0) {
@@ -1239,6 +1261,8 @@ SFL_FN void env_run(SFL_K, int env_id, unsigned stage, char *host_scratch) {
     c->n_tick_logged = h->n_tick_logged; c->n_ep_logged = h->n_ep_logged; c->elapsed = h->elapsed;
     c->aborted = h->aborted; c->reserved = 0;
     c->forced_stops = h->forced_stops; c->stop_actions = h->stop_actions; c->arrived_trains = h->arrived_trains; c->reserved2 = 0;
+    SFL_UA
+    for (int i = 0; i < 6; i++) c->phase_cycles[i] = h->ph[i];
   }
 #if SFL_DEV
   g.sync();

@@ -464,3 +464,24 @@ def test_cuda_shared_table_overlapped_schedule_equals_the_serial_host_run():
     assert np.array_equal(dev.counters()["decisions"], host.counters()["decisions"])
     assert np.array_equal(dev.shared_q_table(), host.shared_q_table())
     dev.close(); host.close()
+
+
+def test_cuda_phase_timers_fill_the_reference_accumulators():
+    """switch_env.py:67-73 / main.py:72-78: with ``phase_timers`` the instrumented (full) kernel splits its time into train
+    ticks, observe, action selection, update and reset; the run itself is the run of the production kernel."""
+    from switchfl_b200 import api
+    fx, _ = load_golden("slips24_t6")
+    hp = dict(gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0, seed=11)
+    out = []
+    for timers in (False, True):
+        env = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=64, device="cuda:0", ep_cap=16, phase_timers=timers)
+        m = api.DistrQLearning(env=env, **hp)
+        m.learn(num_episodes=12, out_dir=None, checkpoint_freq=0)
+        out.append((env, m))
+    (e0, m0), (e1, m1) = out
+    assert np.array_equal(m0.metrics["cum_reward"], m1.metrics["cum_reward"]) and m0.q_table == m1.q_table
+    assert "KIND=full" in e1.engine.kernel_variant() and "KIND=learn" in e0.engine.kernel_variant()
+    parts = [e1.flatland_step_time, e1.last_time, e1.action_selection_time, e1.update_time, e1.reset_time]
+    assert all(p > 0 for p in parts) and sum(parts) <= e1.step_time * (1 + 1e-9)
+    assert e0.step_time > 0 and e0.flatland_step_time == 0.0
+    e0.engine.close(); e1.engine.close()

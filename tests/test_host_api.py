@@ -377,3 +377,20 @@ def test_shared_table_two_ranks_allreduce_equals_one_process(overlapped):
         assert out.returncode == 0, out.stderr[-2000:]
         q0, q1 = np.load(os.path.join(tmp, "q0.npy")), np.load(os.path.join(tmp, "q1.npy"))
     assert np.array_equal(q0, q1) and np.array_equal(q0, want)
+
+
+def test_learn_does_not_depend_on_the_episode_log_capacity():
+    """learn() cuts a run into ep_cap-sized launches with an sfl_reset in between; RailNetwork.reset (rail_network.py:135-149)
+    never clears _train_prev_port / _train_source_port, so neither does a reset that continues a run: one episode per launch
+    gives exactly what one launch for all episodes gives (metrics, Q-table)."""
+    fx, _ = load_golden("slips24_t6")
+    out = []
+    for cap in (1, 16):
+        env = EmulSwitchEnv(api.RailEnv(fx), render_mode=None, max_steps=100_000, n_envs=3, q_cap=4096, ep_cap=cap)
+        m = api.DistrQLearning(env=env, gamma=0.95, epsilon=0.5, epsilon_decay_rate=0.999, lr=0.2, lr_decay_rate=1.0, default_q=0.0, seed=5)
+        m.learn(num_episodes=7, out_dir=None, checkpoint_freq=0)
+        out.append(m)
+    a, b = out
+    for k in ("cum_reward", "arrived_trains", "delays", "num_malfunctions"):
+        assert np.array_equal(a.metrics[k], b.metrics[k]), k
+    assert a.q_table == b.q_table and len(a.q_table) > 0
