@@ -19,7 +19,7 @@ from switchfl_b200 import api, mapgen  # noqa: E402
 
 n_ep = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 512
-fx = mapgen.make_fixture(n=80, n_trains=15, n_chords=50, seed=64, num_cities=25, name="c3_synth80_s64", p_slip=0.3)
+fx = mapgen.c3_fixture(64)                                  # the C3 benchmark map (hyperparam_tuning.py's ENV section, seed 64)
 env = api.ASyncSwitchEnv(api.RailEnv(fx), render_mode=None, max_steps=100_000, n_envs=B, q_cap=65536, ep_cap=256)
 model = api.DistrQLearning(env=env, gamma=1.0, epsilon=0.5, epsilon_decay_rate=0.9997, lr=0.1, lr_decay_rate=1.0, default_q=0.0, seed=64)
 t0 = time.time()
@@ -27,7 +27,7 @@ model.learn(num_episodes=n_ep, out_dir=None, checkpoint_freq=10 ** 9, exploit_fr
 wall = time.time() - t0
 m = model.metrics
 arr, cum = m["arrived_trains"], m["cum_reward"]
-print(f"map c3_synth80_s64: 80x80, 15 trains, {env.rail_map.tab.S} switches; {B} environments (seeds 64..{64 + B - 1}), {n_ep} episodes each; "
+print(f"map {fx['name']}: 80x80, 15 trains, {env.rail_map.tab.S} switches; {B} environments (seeds 64..{64 + B - 1}), {n_ep} episodes each; "
       f"{model.total_decisions:.3e} decisions in {wall:.1f} s wall ({model.total_decisions / wall:.3e}/s incl. host logging)")
 print(f"{'episodes':>14} {'arrived (mean of 15)':>22} {'cum. reward (mean)':>20}")
 edges = [0, 10, 50, 100, 250, 500, 1000, 2000, 3000, 5000, 10000]
