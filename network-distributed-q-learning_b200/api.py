@@ -233,11 +233,26 @@ class DistrQLearning:
         self.ticks_per_launch = 512
         self.dist = dist                       # torch.distributed (initialised) for the shared-table all-reduce, else None
         self.primary_env = 0                 # the env whose curves / Q-table go to the reference-named files
-        self.q_table: Dict[tuple, List[float]] = {}
+        self._q_table: Dict[tuple, List[float]] = {}
+        self._q_stale = False                # the device tables are newer than _q_table (learn() / test() ran)
         self.total_decisions = 0
         self._q_inited = False
         self._table_dirty = False            # device tables hold rows created before q-init (load() / test())
         self._stream_fresh = True
+
+    @property
+    def q_table(self) -> Dict[tuple, List[float]]:
+        """The reference's ``q_table`` dict (distr_q.py:42) of the primary environment.  The tables live on the device;
+        after ``learn()`` / ``test()`` the dict is read back on first use (``save()``, the host-side learner methods, ...)."""
+        if self._q_stale:
+            p = self.primary_env
+            self._q_table = self.env.engine.export_q(p, include_init=self._q_inited, default_q=self._default_q_of(p))
+            self._q_stale = False
+        return self._q_table
+
+    @q_table.setter
+    def q_table(self, q):
+        self._q_table, self._q_stale = q, False
 
     # ------------------------------------------------------------------ internals
     def _hparams(self, episodes: int, episode_base: int = 0):
@@ -364,7 +379,7 @@ class DistrQLearning:
                 cum_reward_exploit.append(r)
                 arrived_exploit.append(a)
             if checkpoint_freq and (cut + 1) % checkpoint_freq == 0 and out_dir:
-                self.q_table = eng.export_q(p, include_init=self._q_inited, default_q=self._default_q_of(p))
+                self._q_stale = True
                 self.save(os.path.join(out_dir, f"checkpoint_{cut + 1}.pkl"))
                 np.savez_compressed(os.path.join(out_dir, f"cum_reward_checkpoint_{cut + 1}.npz"), x=cum_reward[p])
                 np.savez_compressed(os.path.join(out_dir, f"arrived_trains_checkpoint_{cut + 1}.npz"), x=arrived[p, :cut])
@@ -372,7 +387,7 @@ class DistrQLearning:
                 np.savez_compressed(os.path.join(out_dir, f"trains_at_dest_checkpoint_{cut + 1}.npz"), x=[])
                 np.savez_compressed(os.path.join(out_dir, f"num_malfunctions_checkpoint_{cut + 1}.npz"), x=num_malf[p, :cut])
         self._table_dirty = True
-        self.q_table = eng.export_q(p, include_init=self._q_inited, default_q=self._default_q_of(p))
+        self._q_stale = True                 # q_table is read back from the device when it is next used
         at_dest = [[h for h in range(T) if (int(mk) >> h) & 1] for mk in last_mask] if num_episodes else [[] for _ in range(B)]
         self.metrics = dict(cum_reward=cum_reward, arrived_trains=arrived, delays=delays, num_malfunctions=num_malf, trains_at_dest=at_dest,
                             cum_reward_exploit=np.array(cum_reward_exploit), arrived_trains_exploit=np.array(arrived_exploit),
@@ -433,7 +448,7 @@ class DistrQLearning:
                 np.savez_compressed(os.path.join(out_dir, "delays.npz"), x=list(delays[p]))
         if _batched:
             return cum, arr, delays
-        self.q_table = eng.export_q(p, include_init=self._q_inited, default_q=self._default_q_of(p))   # test() inserts rows (App. A #15)
+        self._q_stale = True                 # test() inserts rows (App. A #15)
         return float(cum[p]), int(arr[p]), list(delays[p])
 
     # ------------------------------------------------------------------ distr_q.py:400-490, on the host dict
