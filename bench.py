@@ -434,15 +434,19 @@ def run_e2e(cx: Ctx, wl: str, args, ticks: int, episodes: int) -> dict:
         m = api.DistrQLearning(env=env, seeds=np.arange(Bp, dtype=np.uint64) + np.uint64(SEED + cx.rank * B + k * Bp), dist=cx.dist, **HP)
         m.ticks_per_launch = ticks
         models.append(m)
-    for m in models:                                                      # warm-up: one short learn() (allocations, first launches)
-        m.learn(num_episodes=1, out_dir=None, checkpoint_freq=0)
+    def learn_all(n_ep):
+        if len(models) > 1:                                               # several maps: concurrently, one stream per learner
+            api.learn_concurrently(models, n_ep, None, 0, None)
+        else:
+            models[0].learn(num_episodes=n_ep, out_dir=None, checkpoint_freq=0)
+
+    learn_all(1)                                                          # warm-up: one short learn() (allocations, first launches)
     for m in models:
         m.env.engine.reset_io_counters()
         m.total_decisions = 0
     cx.barrier()
     w0 = time.perf_counter()
-    for m in models:
-        m.learn(num_episodes=episodes, out_dir=None, checkpoint_freq=0)
+    learn_all(episodes)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - w0
     dec = sum(m.total_decisions for m in models)
@@ -455,7 +459,8 @@ def run_e2e(cx: Ctx, wl: str, args, ticks: int, episodes: int) -> dict:
     torch.cuda.empty_cache()
     (e2e_s,), (dec,) = cx.reduce([e2e_s], [dec])
     return {"value": dec / e2e_s, "unit": "decisions/s", "h2d_bytes_per_step": h2d // max(launches, 1), "d2h_bytes_per_step": d2h // max(launches, 1),
-            "api": f"DistrQLearning.learn(num_episodes={episodes}, out_dir=None, checkpoint_freq=0) per map", "wall_s": e2e_s,
+            "api": (f"DistrQLearning.learn(num_episodes={episodes}, out_dir=None, checkpoint_freq=0)" if len(fxs) == 1 else
+                    f"api.learn_concurrently({len(fxs)} learners, num_episodes={episodes}): learn() per map, one thread + stream each"), "wall_s": e2e_s,
             "launches": launches, "step": f"one k_run launch of {ticks} ticks; bytes are the totals copied inside learn() divided by its launches"}
 
 

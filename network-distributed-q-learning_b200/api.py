@@ -514,3 +514,38 @@ class DistrQLearning:
             eng.import_q(i, self.q_table)
         self._table_dirty = True
         self._q_inited = False
+
+
+def learn_concurrently(models: Sequence[DistrQLearning], num_episodes: int, out_dirs: Optional[Sequence[Optional[str]]] = None,
+                       checkpoint_freq: int = 0, exploit_freq: Optional[int] = None) -> None:
+    """``learn()`` of several independent learners (different maps / seeds) at the same time on one GPU: one host thread and
+    one CUDA stream per learner, so that their kernel launches overlap.  This is hyperparam_tuning.py:85-91 -- every
+    (point, seed) run started at once, no communication -- with streams in place of OS processes; the results are those of
+    calling ``learn()`` on each model in turn."""
+    import threading
+    import torch
+    out_dirs = list(out_dirs) if out_dirs is not None else [None] * len(models)
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()                       # buffers were created on the default stream
+    errors: List[BaseException] = []
+
+    def work(m: DistrQLearning, out_dir: Optional[str]):
+        try:
+            dev = m.env.engine.device
+            if dev.type == "cuda":
+                stream = torch.cuda.Stream(device=dev)
+                with torch.cuda.device(dev), torch.cuda.stream(stream):
+                    m.learn(num_episodes, out_dir, checkpoint_freq, exploit_freq)
+                    stream.synchronize()
+            else:
+                m.learn(num_episodes, out_dir, checkpoint_freq, exploit_freq)
+        except BaseException as ex:                    # re-raised in the caller's thread
+            errors.append(ex)
+
+    threads = [threading.Thread(target=work, args=(m, d)) for m, d in zip(models, out_dirs)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]

@@ -25,7 +25,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import mapgen, sharding
-from .api import ASyncSwitchEnv, DistrQLearning, MalfunctionParameters, ParamMalfunctionGen, RailEnv
+from .api import ASyncSwitchEnv, DistrQLearning, MalfunctionParameters, ParamMalfunctionGen, RailEnv, learn_concurrently
 
 
 def fixture_from_env_section(env: Dict[str, str], seed: int) -> dict:
@@ -102,6 +102,7 @@ def launch_grid(hyperparams: Dict[str, Sequence[float]], random_seeds: Sequence[
     device = device or default_device()
     lo, hi = sharding.shard_range(len(random_seeds), rank, world_size)
     written = []
+    runs = []
     for rdx in range(lo, hi):
         seed = int(random_seeds[rdx])
         fx = fixture_from_env_section({k: str(v) for k, v in env_section.items()}, seed)
@@ -113,7 +114,10 @@ def launch_grid(hyperparams: Dict[str, Sequence[float]], random_seeds: Sequence[
         model = DistrQLearning(env=env, gamma=gamma, epsilon=col("epsilon", 0.4), epsilon_decay_rate=col("epsilon_decay_rate", 0.0),
                                lr=col("lr", 0.4), lr_decay_rate=col("lr_decay_rate", 0.0), default_q=default_q,
                                seeds=np.full(len(points), seed, np.uint64))          # same seed for every point, as the reference
-        model.learn(num_episodes=num_episodes, out_dir=None, checkpoint_freq=checkpoint_freq, exploit_freq=exploit_freq)
+        runs.append((rdx, seed, model))
+    # hyperparam_tuning.py:85-91 starts every run at once; here the seeds of this rank learn concurrently, one stream each
+    learn_concurrently([m for _, _, m in runs], num_episodes, None, checkpoint_freq, exploit_freq)
+    for rdx, seed, model in runs:
         for idx, params in enumerate(points):
             exp_dir = os.path.join(out_dir, f"exp_{idx}", f"seed_{rdx}")
             os.makedirs(exp_dir, exist_ok=True)
@@ -127,7 +131,7 @@ def launch_grid(hyperparams: Dict[str, Sequence[float]], random_seeds: Sequence[
                 config.write(f)
             model.write_outputs(idx, exp_dir, exploit=exploit_freq is not None)
             written.append(exp_dir)
-        env.engine.close()
+        model.env.engine.close()
     return written
 
 

@@ -713,7 +713,7 @@ int sfl_run(void *ctx, int mode, int max_ticks, void *stream) {
   k<<<grid, threads, smem, (cudaStream_t)stream>>>(K);
   CU(cudaGetLastError());
 #else
-  static char host_scratch[32 * SFL_MAX_T + 2 * SFL_MAX_T + 64];
+  static thread_local char host_scratch[32 * SFL_MAX_T + 2 * SFL_MAX_T + 64];
   for (int i = 0; i < c->cfg.n_envs; i++) {
     if (c->cfg.shared_q) {
       if (trace) return fail(SFL_E_ARG, "shared-table mode has no trace / step variants%s");

@@ -490,3 +490,24 @@ def test_cuda_phase_timers_fill_the_reference_accumulators():
     assert all(p > 0 for p in parts) and sum(parts) <= e1.step_time * (1 + 1e-9)
     assert e0.step_time > 0 and e0.flatland_step_time == 0.0
     e0.engine.close(); e1.engine.close()
+
+
+def test_cuda_learn_concurrently_equals_learning_in_turn():
+    """api.learn_concurrently: one host thread + CUDA stream per learner (different maps); same results as learn() in turn."""
+    from switchfl_b200 import api
+    fxs = [load_golden(n)[0] for n in ("c1_synth18", "slips24_t6", "c3_rail80_s64")]
+
+    def models():
+        out = []
+        for k, fx in enumerate(fxs):
+            env = api.ASyncSwitchEnv(api.RailEnv(fx), max_steps=100_000, n_envs=32, device="cuda:0", ep_cap=8)
+            out.append(api.DistrQLearning(env=env, gamma=0.95, epsilon=0.5, epsilon_decay_rate=0.999, lr=0.2, lr_decay_rate=1.0, default_q=0.0, seed=50 + k))
+        return out
+    a, b = models(), models()
+    for m in a:
+        m.learn(num_episodes=6, out_dir=None, checkpoint_freq=0)
+    api.learn_concurrently(b, 6)
+    for x, y in zip(a, b):
+        assert np.array_equal(x.metrics["cum_reward"], y.metrics["cum_reward"]) and np.array_equal(x.metrics["delays"], y.metrics["delays"])
+        assert x.q_table == y.q_table and len(x.q_table) > 0
+        x.env.engine.close(); y.env.engine.close()

@@ -394,3 +394,23 @@ def test_learn_does_not_depend_on_the_episode_log_capacity():
     for k in ("cum_reward", "arrived_trains", "delays", "num_malfunctions"):
         assert np.array_equal(a.metrics[k], b.metrics[k]), k
     assert a.q_table == b.q_table and len(a.q_table) > 0
+
+
+def test_learn_concurrently_equals_learning_in_turn():
+    """api.learn_concurrently (hyperparam_tuning.py's fan-out on streams / threads): same metrics and Q-tables as learn() per
+    model in turn."""
+    fxs = [load_golden(n)[0] for n in ("c1_synth18", "slips24_t6", "loop_chord_7x7")]
+
+    def models():
+        out = []
+        for k, fx in enumerate(fxs):
+            env = EmulSwitchEnv(api.RailEnv(fx), render_mode=None, max_steps=100_000, n_envs=3, q_cap=4096, ep_cap=8)
+            out.append(api.DistrQLearning(env=env, gamma=0.95, epsilon=0.5, epsilon_decay_rate=0.999, lr=0.2, lr_decay_rate=1.0, default_q=0.0, seed=50 + k))
+        return out
+    a, b = models(), models()
+    for m in a:
+        m.learn(num_episodes=5, out_dir=None, checkpoint_freq=0)
+    api.learn_concurrently(b, 5)
+    for x, y in zip(a, b):
+        assert np.array_equal(x.metrics["cum_reward"], y.metrics["cum_reward"]) and np.array_equal(x.metrics["delays"], y.metrics["delays"])
+        assert x.q_table == y.q_table and len(x.q_table) > 0
