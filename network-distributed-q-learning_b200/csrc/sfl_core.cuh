@@ -1267,8 +1267,7 @@ SFL_FN void env_run(SFL_K, int env_id, unsigned stage, char *host_scratch) {
           const int t = more ? h->dec_t : 0;
           const int semb = observe_bits(K, e, g, more, t);
           if (more && g.gl == 0) decide<KIND>(K, e, hp, env_id, t, semb);
-          g.sync();
-        }
+        }                                                                 // (the sync at the top of the next round orders the first lane's stores)
         if (due && g.gl == 0 && (h->terminated || h->truncated)) episode_end(K, e, env_id);
       } else if (due && g.gl == 0) {
         SFL_NU
