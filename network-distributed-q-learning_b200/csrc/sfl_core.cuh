@@ -21,10 +21,9 @@
 #if defined(__CUDACC__) && !defined(SFL_HOST_EMUL)
 #define SFL_DEV 1
 #define SFL_FN __device__ __forceinline__
-#define SFL_NI __device__ __forceinline__
+#define SFL_NI __device__ __forceinline__          // the Q probe / update: inline (see SFL_RARE)
 #define SFL_RARE __device__ __noinline__          // once-per-episode paths: out of line (instruction cache), even though a
                                                   // noinline callee reads the kernel parameter block through a generic pointer
-#define SFL_CONST __constant__
 #define SFL_NU _Pragma("unroll 1")
 #define SFL_U4 _Pragma("unroll 4")
 #define SFL_UA _Pragma("unroll")
@@ -35,7 +34,6 @@
 #define SFL_FN inline
 #define SFL_NI inline
 #define SFL_RARE inline
-#define SFL_CONST static
 #define SFL_NU
 #define SFL_U4
 #define SFL_UA
